@@ -1,0 +1,154 @@
+"""ctypes wrapper of oracle/remap_oracle.c (the CPU restatement).  TEST INFRASTRUCTURE ONLY.
+
+Never imported by the product path (remap_b200/); only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline leg use it, as the checker.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "remap_oracle.c")
+LIB = os.path.join(HERE, "_build", "libremap_oracle.so")
+
+KP_DTYPE = np.dtype([("code", "u1", (13,)), ("weight", "u1"), ("x", "<u2"), ("y", "<u2"),
+                     ("region_mask", "<u4")], align=True)
+BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
+VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
+                       ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
+                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,))])
+RESULT_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("valid", "<u4"), ("tie_sensitive", "<u4"),
+                         ("active", "<u4"), ("top_dx", "<i4", (2,)), ("top_dy", "<i4", (2,)),
+                         ("top_score", "<u4", (2,)), ("ntop", "<u4")])
+
+
+class Config(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in
+                ("width", "height", "grid_w", "grid_h", "overlap", "weight_switch", "region_votes")]
+
+
+def config(width, height, grid_w=4, grid_h=2, overlap=16, weight_switch=10, region_votes=3):
+    """Defaults are the reference's constants: src/frc.hpp:22-24,32-33."""
+    return Config(width, height, grid_w, grid_h, overlap, weight_switch, region_votes)
+
+
+def build(force=False):
+    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(SRC):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-Wall", "-o", LIB, SRC])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.ro_extract.restype = C.c_size_t
+        _lib.ro_extract.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.ro_match.restype = None
+        _lib.ro_match.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                  C.c_void_p, C.c_void_p]
+        _lib.ro_region_bins.restype = C.c_size_t
+        _lib.ro_region_bins.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.c_uint32, C.c_void_p, C.c_size_t]
+        _lib.ro_register.restype = C.c_size_t
+        _lib.ro_register.argtypes = [C.POINTER(Config), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+        _lib.ro_foreground_mask.restype = None
+        _lib.ro_foreground_mask.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
+                                            C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.ro_luts.restype = None
+        _lib.ro_luts.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.ro_sections.restype = None
+        _lib.ro_sections.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
+        for fn, dt in (("ro_sizeof_keypoint", KP_DTYPE), ("ro_sizeof_region_vote", VOTE_DTYPE),
+                       ("ro_sizeof_match_result", RESULT_DTYPE)):
+            f = getattr(_lib, fn)
+            f.restype = C.c_size_t
+            assert f() == dt.itemsize, (fn, f(), dt.itemsize)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def luts():
+    n2o = np.zeros(16, np.uint8)
+    o2n = np.zeros(16, np.uint8)
+    lib().ro_luts(_p(n2o), _p(o2n))
+    return n2o, o2n
+
+
+def sections(cfg):
+    cs = np.zeros(cfg.width, np.uint32)
+    rs = np.zeros(cfg.height, np.uint32)
+    lib().ro_sections(C.byref(cfg), _p(cs), _p(rs))
+    return cs, rs
+
+
+def extract(cfg, frame):
+    """-> (median (H, W) u8, keypoints structured array in the reference's insertion order)."""
+    frame = np.ascontiguousarray(frame, np.uint8)
+    H, W = frame.shape
+    assert (W, H) == (cfg.width, cfg.height)
+    median = np.zeros((H, W), np.uint8)
+    kps = np.zeros(W * H, KP_DTYPE)
+    n = lib().ro_extract(C.byref(cfg), _p(frame), _p(median), _p(kps), kps.shape[0])
+    return median, kps[:n].copy()
+
+
+def match(cfg, prev_kps, curr_kps):
+    """-> (result record, per-region vote records)."""
+    prev_kps = np.ascontiguousarray(prev_kps)
+    curr_kps = np.ascontiguousarray(curr_kps)
+    res = np.zeros(1, RESULT_DTYPE)
+    votes = np.zeros(cfg.grid_w * cfg.grid_h, VOTE_DTYPE)
+    lib().ro_match(C.byref(cfg), _p(prev_kps), prev_kps.shape[0], _p(curr_kps), curr_kps.shape[0],
+                   _p(res), _p(votes))
+    return res[0], votes
+
+
+def region_bins(cfg, prev_kps, curr_kps, region):
+    prev_kps = np.ascontiguousarray(prev_kps)
+    curr_kps = np.ascontiguousarray(curr_kps)
+    cap = 1 << 16
+    while True:
+        bins = np.zeros(cap, BIN_DTYPE)
+        n = lib().ro_region_bins(C.byref(cfg), _p(prev_kps), prev_kps.shape[0], _p(curr_kps),
+                                 curr_kps.shape[0], region, _p(bins), cap)
+        if n <= cap:
+            return bins[:n].copy()
+        cap = int(n)
+
+
+def register(cfg, frames, want_medians=False):
+    """The frc loop over a whole sequence.
+    -> dict(results (N-1,) RESULT_DTYPE, positions (N,3) i32 [fragment,x,y], medians|None, kp_counts (N,))"""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    N, H, W = frames.shape
+    assert (W, H) == (cfg.width, cfg.height)
+    results = np.zeros(max(N - 1, 0), RESULT_DTYPE)
+    positions = np.zeros((N, 3), np.int32)
+    medians = np.zeros((N, H, W), np.uint8) if want_medians else None
+    kpc = np.zeros(N, np.uint32)
+    total = lib().ro_register(C.byref(cfg), _p(frames), N, _p(results), _p(positions), _p(medians), _p(kpc))
+    return dict(results=results, positions=positions, medians=medians, kp_counts=kpc, total_keypoints=int(total))
+
+
+def foreground_mask(bg, px, py, frame):
+    bg = np.ascontiguousarray(bg, np.uint8)
+    frame = np.ascontiguousarray(frame, np.uint8)
+    bh, bw = bg.shape
+    H, W = frame.shape
+    mask = np.zeros((H, W), np.uint8)
+    lib().ro_foreground_mask(_p(bg), bw, bh, px, py, _p(frame), W, H, _p(mask))
+    return mask

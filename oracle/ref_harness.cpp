@@ -1,0 +1,335 @@
+// oracle/ref_harness.cpp -- harness around the REAL reference (kataklinger/remap) headers.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle/build_ref.py).  This file is ours; it #includes the
+// reference's own headers (patched for GCC in a temp dir at build time) and calls the
+// reference's own functions:
+//   kpe::extractor<frc::grid_type, frc::grid_overlap>::extract   (src/kpe.hpp:92-108)
+//   kpm::match(cfg, prev_grid, curr_grid)                        (src/kpm.hpp:395-415)
+//   kpm::details::count_offsets / top_offsets                    (src/kpm.hpp:105-159)
+//   frc::collector::collect                                      (src/frc.hpp:55-68)
+//   fde::details::generate_mask                                  (src/fde.hpp:19-55)
+//   nic::compress                                                (src/nic.hpp:8-105)
+//
+// Modes
+//   dump  <frames.bin> W H N <out.bin>      canonical dump of every intermediate (see below)
+//   bench <frames.bin> W H N <reg|frc> T R  time the reference on T host threads, R repeats
+//   mask  <bg.bin> bgW bgH px py <frame.bin> W H <out.bin>
+//
+// frames.bin = N*H*W bytes, row-major, values 0..15 (== nil::read_raw format, src/nil.hpp:24).
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <map>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "fde.hpp"
+#include "frc.hpp"
+#include "nic.hpp"
+
+namespace {
+
+using pixel_alloc_t = frc::allocator_t<cpl::nat_cc>;
+using extractor_t = kpe::extractor<frc::grid_type, frc::grid_overlap>;
+
+// Same constants as the private frc::collector::match_config (src/frc.hpp:30-44).
+struct match_config {
+  using allocator_type = frc::allocator_t<char>;
+  static constexpr std::size_t weight_switch{10};
+  static constexpr std::size_t region_votes{3};
+  explicit match_config(allocator_type const& a) noexcept : allocator_{a} {}
+  [[nodiscard]] allocator_type get_allocator() const noexcept { return allocator_; }
+  allocator_type allocator_;
+};
+
+std::vector<std::uint8_t> read_file(char const* path, std::size_t expect) {
+  std::vector<std::uint8_t> buf(expect);
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { std::fprintf(stderr, "cannot open %s\n", path); std::exit(2); }
+  std::size_t got = std::fread(buf.data(), 1, expect, f);
+  std::fclose(f);
+  if (got != expect) { std::fprintf(stderr, "%s: short read %zu < %zu\n", path, got, expect); std::exit(2); }
+  return buf;
+}
+
+// In-memory feed satisfying ifd::feeder (src/ifd.hpp:20-28).
+class memory_feed {
+public:
+  memory_feed(std::uint8_t const* data, std::size_t w, std::size_t h, std::size_t first, std::size_t last)
+      : data_{data}, dim_{w, h}, next_{first}, last_{last} {}
+  [[nodiscard]] bool has_more() const noexcept { return next_ < last_; }
+  template<typename Alloc>
+  [[nodiscard]] auto produce(Alloc const& alloc) {
+    using image_type = sid::nat::aimg_t<Alloc>;
+    image_type img{dim_, alloc};
+    std::memcpy(img.data(), data_ + next_ * dim_.area(), dim_.area());
+    return ifd::frame<image_type>{next_++, std::move(img)};
+  }
+private:
+  std::uint8_t const* data_;
+  mrl::dimensions_t dim_;
+  std::size_t next_, last_;
+};
+
+struct null_compression {
+  template<typename Alloc>
+  [[nodiscard]] icd::compressed_t operator()(sid::nat::aimg_t<Alloc> const&) const { return {}; }
+};
+struct native_compression {  // what main.cpp uses (src/main.cpp:112-125)
+  template<typename Alloc>
+  [[nodiscard]] icd::compressed_t operator()(sid::nat::aimg_t<Alloc> const& image) const {
+    return nic::compress(image);
+  }
+};
+
+void put32(FILE* f, std::uint32_t v) { std::fwrite(&v, 4, 1, f); }
+void puti32(FILE* f, std::int32_t v) { std::fwrite(&v, 4, 1, f); }
+
+struct kp_rec { std::uint16_t x, y; std::uint8_t code[13]; };
+
+void dump_grid(FILE* out, frc::grid_type const& grid) {
+  for (auto& region : grid.regions()) {
+    std::vector<kp_rec> recs;
+    for (auto& [code, pts] : region.points()) {
+      for (auto& p : pts) {
+        kp_rec r;
+        r.x = static_cast<std::uint16_t>(p.x_);
+        r.y = static_cast<std::uint16_t>(p.y_);
+        std::memcpy(r.code, code.data(), 13);
+        recs.push_back(r);
+      }
+    }
+    std::sort(recs.begin(), recs.end(), [](kp_rec const& a, kp_rec const& b) {
+      return a.x != b.x ? a.x < b.x : a.y < b.y;
+    });
+    put32(out, static_cast<std::uint32_t>(recs.size()));
+    put32(out, static_cast<std::uint32_t>(region.counts()[1]));
+    put32(out, static_cast<std::uint32_t>(region.counts()[2]));
+    for (auto& r : recs) {
+      std::fwrite(&r.x, 2, 1, out);
+      std::fwrite(&r.y, 2, 1, out);
+      std::fwrite(r.code, 1, 13, out);
+    }
+  }
+}
+
+template<typename Alloc>
+void dump_pair(FILE* out, frc::grid_type const& prev, frc::grid_type const& curr, Alloc const& alloc) {
+  match_config cfg{alloc};
+  auto off = kpm::match(cfg, prev, curr);  // the reference's own declaration
+  put32(out, off ? 1u : 0u);
+  puti32(out, off ? off->x_ : 0);
+  puti32(out, off ? off->y_ : 0);
+  put32(out, static_cast<std::uint32_t>(kpm::details::get_active(curr)));
+
+  auto pregs{prev.regions()}, cregs{curr.regions()};
+  for (std::size_t i = 0; i < frc::grid_type::region_count; ++i) {
+    // same switch as kpm::details::cast_vote (src/kpm.hpp:217-222)
+    bool use_all = pregs[i].counts()[2] < match_config::weight_switch ||
+                   cregs[i].counts()[2] <= match_config::weight_switch;
+    auto total = use_all ? kpm::details::count_offsets<true>(cfg, pregs[i], cregs[i])
+                         : kpm::details::count_offsets<false>(cfg, pregs[i], cregs[i]);
+    auto ticket = kpm::details::top_offsets(cfg, total, match_config::region_votes);
+
+    std::map<std::pair<std::int32_t, std::int32_t>, std::uint32_t> sorted;
+    for (auto& [o, c] : total) sorted[{o.x_, o.y_}] = static_cast<std::uint32_t>(c);
+    put32(out, use_all ? 1u : 0u);
+    put32(out, static_cast<std::uint32_t>(sorted.size()));
+    for (auto& [o, c] : sorted) { puti32(out, o.first); puti32(out, o.second); put32(out, c); }
+    put32(out, static_cast<std::uint32_t>(ticket.size()));
+    for (auto& v : ticket) {
+      puti32(out, v.offset_.x_); puti32(out, v.offset_.y_);
+      put32(out, static_cast<std::uint32_t>(v.count_));
+    }
+  }
+}
+
+int run_dump(int argc, char** argv) {
+  if (argc < 7) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  auto frames = read_file(argv[2], N * W * H);
+  FILE* out = std::fopen(argv[6], "wb");
+  if (!out) return 2;
+  std::fwrite("RMDP", 1, 4, out);
+  put32(out, W); put32(out, H); put32(out, N);
+
+  // section 1: per frame median + grid; per pair votes and the declared offset
+  {
+    extractor_t extractor{mrl::dimensions_t{W, H}};
+    all::memory_stack<cpl::nat_cc> memory{};
+    memory_feed feed{frames.data(), W, H, 0, N};
+
+    auto first_alloc{memory.previous()};
+    auto frame{feed.produce(first_alloc)};
+    frc::image_type median{frame.image_.dimensions(), first_alloc};
+    auto pkeys{extractor.extract(frame.image_, median, first_alloc)};
+    std::fwrite(median.data(), 1, W * H, out);
+    dump_grid(out, pkeys);
+
+    while (feed.has_more()) {
+      all::memory_swing swing{memory};
+      pixel_alloc_t alloc{swing};
+      auto fr{feed.produce(alloc)};
+      frc::image_type med{fr.image_.dimensions(), alloc};
+      auto keys{extractor.extract(fr.image_, med, alloc)};
+      std::fwrite(med.data(), 1, W * H, out);
+      dump_grid(out, keys);
+      dump_pair(out, pkeys, keys, alloc);
+      pkeys = std::move(keys);
+    }
+  }
+
+  // section 2: the unmodified frc::collector loop -> (fragment index, position) per frame
+  {
+    frc::collector collector{mrl::dimensions_t{W, H}};
+    memory_feed feed{frames.data(), W, H, 0, N};
+    std::vector<std::int32_t> rec(3 * N, 0);  // fragment, x, y per frame (frame 0 is (0,0,0))
+    collector.collect(feed, null_compression{},
+                      [&](fgm::fragment const& frag, frc::frame_type const& fr,
+                          frc::image_type const&, frc::grid_type const&) {
+                        auto& pos = frag.frames().back().position_;  // raw, before normalize()
+                        rec[3 * fr.number_ + 1] = pos.x_;
+                        rec[3 * fr.number_ + 2] = pos.y_;
+                      });
+    auto frags = collector.complete();
+    std::int32_t fi = 0;
+    for (auto& f : frags) {
+      for (auto& fr : f.frames()) rec[3 * fr.number_] = fi;
+      ++fi;
+    }
+    put32(out, static_cast<std::uint32_t>(rec.size() / 3));
+    std::fwrite(rec.data(), 4, rec.size(), out);
+  }
+  std::fclose(out);
+  return 0;
+}
+
+// ---- bench ------------------------------------------------------------------------------
+struct shard_result { double seconds; std::size_t frames; std::size_t keypoints; std::int64_t checksum; };
+
+shard_result bench_reg(std::uint8_t const* frames, std::size_t W, std::size_t H, std::size_t first, std::size_t last) {
+  // kpe + kpm + position accumulation only (the registration path this repo replaces)
+  auto t0 = std::chrono::steady_clock::now();
+  extractor_t extractor{mrl::dimensions_t{W, H}};
+  all::memory_stack<cpl::nat_cc> memory{};
+  memory_feed feed{frames, W, H, first, last};
+  auto first_alloc{memory.previous()};
+  auto frame{feed.produce(first_alloc)};
+  frc::image_type median{frame.image_.dimensions(), first_alloc};
+  auto pkeys{extractor.extract(frame.image_, median, first_alloc)};
+  std::int64_t px = 0, py = 0, checksum = 0;
+  std::size_t kps = 0;
+  while (feed.has_more()) {
+    all::memory_swing swing{memory};
+    pixel_alloc_t alloc{swing};
+    auto fr{feed.produce(alloc)};
+    frc::image_type med{fr.image_.dimensions(), alloc};
+    auto keys{extractor.extract(fr.image_, med, alloc)};
+    if (auto off{kpm::match(match_config{alloc}, pkeys, keys)}; off) { px += off->x_; py += off->y_; }
+    else { px = py = 0; checksum += 1000003; }
+    checksum += px * 31 + py;
+    for (auto& r : keys.regions()) kps += r.total_count();
+    pkeys = std::move(keys);
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return {std::chrono::duration<double>(t1 - t0).count(), last - first, kps, checksum};
+}
+
+shard_result bench_frc(std::uint8_t const* frames, std::size_t W, std::size_t H, std::size_t first, std::size_t last) {
+  // the reference's whole per-frame loop: kpe + kpm + nic compression x2 + fragment blit
+  auto t0 = std::chrono::steady_clock::now();
+  frc::collector collector{mrl::dimensions_t{W, H}};
+  memory_feed feed{frames, W, H, first, last};
+  std::size_t kps = 0;
+  collector.collect(feed, native_compression{},
+                    [&](fgm::fragment const&, frc::frame_type const&, frc::image_type const&,
+                        frc::grid_type const& g) { for (auto& r : g.regions()) kps += r.total_count(); });
+  auto frags = collector.complete();
+  auto t1 = std::chrono::steady_clock::now();
+  std::int64_t checksum = static_cast<std::int64_t>(frags.size());
+  return {std::chrono::duration<double>(t1 - t0).count(), last - first, kps, checksum};
+}
+
+int run_bench(int argc, char** argv) {
+  if (argc < 9) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  std::string mode = argv[6];
+  std::size_t T = std::atoll(argv[7]), R = std::atoll(argv[8]);
+  auto frames = read_file(argv[2], N * W * H);
+  if (T < 1) T = 1;
+  if (T > N / 2) T = std::max<std::size_t>(1, N / 2);
+  double best = 1e30, total = 0;
+  std::size_t kps = 0, pairs = 0;
+  std::int64_t checksum = 0;
+  for (std::size_t rep = 0; rep < R; ++rep) {
+    std::vector<shard_result> res(T);
+    std::vector<std::thread> th;
+    auto t0 = std::chrono::steady_clock::now();
+    for (std::size_t t = 0; t < T; ++t) {
+      // contiguous shards with a one-frame overlap: every consecutive pair belongs to one shard
+      std::size_t lo = t * N / T, hi = (t + 1) * N / T;
+      std::size_t first = lo == 0 ? 0 : lo - 1;
+      th.emplace_back([&, t, first, hi] {
+        res[t] = mode == "frc" ? bench_frc(frames.data(), W, H, first, hi)
+                               : bench_reg(frames.data(), W, H, first, hi);
+      });
+    }
+    for (auto& x : th) x.join();
+    auto t1 = std::chrono::steady_clock::now();
+    double wall = std::chrono::duration<double>(t1 - t0).count();
+    best = std::min(best, wall);
+    total += wall;
+    kps = 0; checksum = 0;
+    for (auto& r : res) { kps += r.keypoints; checksum += r.checksum; }
+    pairs = N - 1;
+  }
+  std::printf("{\"mode\": \"%s\", \"threads\": %zu, \"frames\": %zu, \"pairs\": %zu, \"reps\": %zu, "
+              "\"best_s\": %.6f, \"mean_s\": %.6f, \"fps_best\": %.3f, \"fps_mean\": %.3f, "
+              "\"keypoint_insertions_per_frame\": %.1f, \"checksum\": %lld}\n",
+              mode.c_str(), T, N, pairs, R, best, total / R, N / best, N / (total / R),
+              double(kps) / double(N > 1 ? N - 1 : 1), static_cast<long long>(checksum));
+  return 0;
+}
+
+int run_mask(int argc, char** argv) {
+  if (argc < 11) return 1;
+  std::size_t bw = std::atoll(argv[3]), bh = std::atoll(argv[4]);
+  std::int32_t px = std::atoi(argv[5]), py = std::atoi(argv[6]);
+  std::size_t W = std::atoll(argv[8]), H = std::atoll(argv[9]);
+  auto bg = read_file(argv[2], bw * bh);
+  auto fr = read_file(argv[7], W * H);
+  sid::nat::dimg_t background{mrl::dimensions_t{bw, bh}};
+  std::memcpy(background.data(), bg.data(), bg.size());
+  sid::nat::dimg_t frame{mrl::dimensions_t{W, H}};
+  std::memcpy(frame.data(), fr.data(), fr.size());
+  sid::mon::dimg_t mask{mrl::dimensions_t{W, H}};
+  auto idx = cdt::to_index(fgm::point_t{px, py}, background.dimensions());  // src/fde.hpp:87
+  if (idx % fde::details::mm_size == 0)                                     // src/fde.hpp:107-114
+    fde::details::generate_mask(background, frame, mask, idx, std::true_type{});
+  else
+    fde::details::generate_mask(background, frame, mask, idx, std::false_type{});
+  FILE* out = std::fopen(argv[10], "wb");
+  if (!out) return 2;
+  std::fwrite(mask.data(), 1, W * H, out);
+  std::fclose(out);
+  return 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::fprintf(stderr, "usage: ref_harness dump|bench|mask ...\n"); return 1; }
+  std::string mode = argv[1];
+  if (mode == "dump") return run_dump(argc, argv);
+  if (mode == "bench") return run_bench(argc, argv);
+  if (mode == "mask") return run_mask(argc, argv);
+  return 1;
+}

@@ -1,0 +1,85 @@
+"""CPU: the C restatement (oracle/remap_oracle.c) against committed dumps of the REAL reference.
+
+This is the oracle's pin (the reference has no test vectors of its own)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import oracle, refdump
+
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+               if not p.endswith("fgmask.npz"))
+
+
+def test_luts_known_answer():
+    # values the reference's consteval LUT generator produces (src/cpl.hpp:163-217), SURVEY.md a1
+    n2o, o2n = oracle.luts()
+    assert n2o.tolist() == [0, 15, 2, 12, 6, 9, 3, 13, 5, 1, 7, 4, 8, 14, 10, 11]
+    assert o2n.tolist() == [0, 9, 2, 6, 11, 8, 4, 10, 12, 5, 14, 15, 3, 7, 13, 1]
+
+
+def _runs(a):
+    out, s = [], 0
+    for i in range(1, len(a) + 1):
+        if i == len(a) or a[i] != a[s]:
+            out.append((s, i, int(a[s])))
+            s = i
+    return out
+
+
+def test_sections_known_answer():
+    # SURVEY.md Appendix A.4 (derived from src/kpe.hpp:157-192,235-277 for 320x224 and 640x480)
+    cs, rs = oracle.sections(oracle.config(320, 224))
+    assert _runs(cs) == [(0, 2, 0), (2, 74, 1), (74, 90, 3), (90, 162, 2), (162, 178, 6), (178, 250, 4),
+                         (250, 266, 12), (266, 318, 8), (318, 320, 0)]
+    assert _runs(rs) == [(0, 2, 0), (2, 107, 1), (107, 123, 3), (123, 220, 2), (220, 224, 0)]
+    cs, rs = oracle.sections(oracle.config(640, 480))
+    assert [r[:2] for r in _runs(cs)] == [(0, 2), (2, 154), (154, 170), (170, 322), (322, 338), (338, 490),
+                                          (490, 506), (506, 638), (638, 640)]
+    assert [r[:2] for r in _runs(rs)] == [(0, 2), (2, 235), (235, 251), (251, 476), (476, 480)]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_dump(name, golden_dir):
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    frames = z["frames"]
+    ref = refdump.parse_dump(z["dump"].tobytes())
+    N, H, W = frames.shape
+    cfg = oracle.config(W, H)
+    prev = None
+    valid, dx, dy = [], [], []
+    flagged = 0
+    for i in range(N):
+        med, kps = oracle.extract(cfg, frames[i])
+        parity.check_frame(ref["frames"][i], med, kps, f"{name} frame {i}")
+        if i > 0:
+            res, votes = oracle.match(cfg, prev, kps)
+            bins = [oracle.region_bins(cfg, prev, kps, r) for r in range(8)]
+            st = parity.check_pair(ref["pairs"][i - 1], res, votes, bins, f"{name} pair {i}")
+            flagged += st == "flagged"
+            valid.append(bool(res["valid"])); dx.append(int(res["dx"])); dy.append(int(res["dy"]))
+        prev = kps
+    if flagged == 0:
+        # the unmodified frc::collector loop's (fragment, x, y) per frame
+        assert np.array_equal(parity.positions_from_results(valid, dx, dy), ref["positions"])
+    if name != "parallax":
+        assert flagged == 0
+    # whole-sequence entry point agrees with the per-frame calls
+    out = oracle.register(cfg, frames, want_medians=True)
+    assert [bool(v) for v in out["results"]["valid"]] == valid
+    assert out["results"]["dx"].tolist() == dx and out["results"]["dy"].tolist() == dy
+    for i in range(N):
+        assert np.array_equal(out["medians"][i], ref["frames"][i]["median"])
+
+
+def test_foreground_mask_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "fgmask.npz"))
+    bg = z["bg"]
+    for k in range(int(z["n"])):
+        px, py = (int(v) for v in z[f"pos{k}"])
+        m = oracle.foreground_mask(bg, px, py, z[f"frame{k}"])
+        assert np.array_equal(m, z[f"mask{k}"])
+        assert set(np.unique(m).tolist()) <= {0, 255}
