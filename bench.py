@@ -1,0 +1,366 @@
+#!/usr/bin/env python3
+"""bench.py -- frames/s registered (kpe + kpm + declare) on N B200s, with roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic 320x224 scrolling tilemap, 20,000 frames per GPU,
+HBM-resident (1.43 GB per GPU, far larger than the 126 MB L2, so every step streams from HBM).
+A STEP is one pass of the hot path over the rank's whole frame range: K1 keypoint extraction on
+every frame, K2 matching + voting on every consecutive pair and region, K3 declaration, and (N > 1)
+the NCCL gather of the 12-byte pair results to rank 0.  Weak scaling: every rank holds its own
+contiguous 20,000-frame range of one global N*20,000-frame sequence, with a one-frame overlap.
+
+value  = frames of all ranks * K / device time (CUDA events on the launching stream, max over ranks)
+e2e    = same metric through the public API with HOST buffers: rb_upload from pinned memory +
+         rb_register + rb_fetch_offsets inside the timed region
+roofline / cpu_baseline / clocks: see the JSON keys; DESIGN.md explains the byte accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec registered (kpe+kpm+kpr)"
+UNIT = "frames/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_shard(args, rank, world):
+    """This rank's contiguous range of the global sequence (one-frame overlap with the predecessor)."""
+    from remap_b200 import shard, synth
+    total = args.frames * world
+    first, end, _, _ = shard.shard_range(total, world, rank)
+    seq = synth.scrolling_tilemap(total, args.width, args.height, seed=args.seed, speckle=args.speckle,
+                                  frame_range=(first, end))
+    return seq, total
+
+
+def cpu_reference(frames, threads, reps=1):
+    """Times the REAL reference (oracle/_ref/ref_harness: kpe::extractor::extract + kpm::match per
+    frame, one independent contiguous shard per host thread) on a bounded sample."""
+    from oracle import refdump
+    if refdump.have_ref():
+        r = refdump.ref_bench(frames, mode="reg", threads=threads, reps=reps)
+        return dict(value=r["fps_best"], kind="reference", cores=r["threads"],
+                    keypoint_insertions_per_frame=r["keypoint_insertions_per_frame"])
+    # the compiled reference did not travel: time the C restatement (single thread)
+    from oracle import oracle
+    cfg = oracle.config(frames.shape[2], frames.shape[1])
+    t0 = time.perf_counter()
+    oracle.register(cfg, frames)
+    dt = time.perf_counter() - t0
+    return dict(value=frames.shape[0] / dt, kind="port", cores=1)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from remap_b200 import synth
+    threads = os.cpu_count() or 1
+    sample = min(args.frames, max(args.cpu_sample, 64 * threads))
+    seq = synth.scrolling_tilemap(sample, args.width, args.height, seed=args.seed, speckle=args.speckle)
+    for _ in range(args.warmup):
+        cpu_reference(seq.frames[: max(sample // 4, 2 * threads)], threads)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_reference(seq.frames, threads)
+        vals.append(r["value"])
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{sample} frames of the same sequence per step, one contiguous shard per host thread "
+                                   "(kpe::extractor::extract + kpm::match per frame, as frc::collector::process_frame does)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, kpf):
+    c = {"workload": f"synthetic {args.width}x{args.height} scrolling tilemap (8x8 tiles, {args.speckle:.0%} speckle, "
+                     f"seed {args.seed}), {args.frames} frames per GPU, kpe+kpm+declare",
+         "frames_per_gpu": args.frames, "width": args.width, "height": args.height,
+         "parallelism": f"frame-range sharding x{args.gpus}, one-frame overlap, NCCL gather of pair results",
+         "l2_policy": "inputs larger than L2 (frame store per GPU = "
+                      f"{args.frames * args.width * args.height / 1e6:.0f} MB vs 126 MB L2); no flush needed"}
+    if kpf is not None:
+        c["keypoints_per_frame"] = kpf
+    return c
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=20000, help="frames per GPU (BASELINE configs[1]: 20,000)")
+    ap.add_argument("--width", type=int, default=320)
+    ap.add_argument("--height", type=int, default=224)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--speckle", type=float, default=0.05)
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="frames of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import remap_b200
+    from remap_b200 import RB_OFFSET_VALID, shard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: remap_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    seq, total_frames = make_shard(args, rank, world)
+    n = seq.frames.shape[0]
+    stream = torch.cuda.Stream(device=dev)
+    reg = remap_b200.Registrar(args.width, args.height, max_frames=n, device=local_rank, compute_median=True,
+                               profile=True, stream=stream.cuda_stream)
+    # pinned host copy of the frames (source of the e2e path; also the one-off resident upload)
+    pinned = torch.empty((n, args.height, args.width), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = seq.frames
+    host_frames = pinned.numpy()
+    pinned_off = torch.empty(((n - 1) * 3,), dtype=torch.int32, pin_memory=True)
+    host_off = pinned_off.numpy().view(remap_b200.OFFSET_DTYPE)
+
+    reg.upload(host_frames)
+    reg.synchronize()
+
+    class _Dev:  # zero-copy torch view of the library's device-side pair results
+        def __init__(self, ptr, nwords):
+            self.__cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    dev_off = torch.as_tensor(_Dev(reg.offsets_device_ptr, (n - 1) * 3), device=dev).view(n - 1, 3)
+    _, _, p0, p1 = shard.shard_range(total_frames, world, rank)
+    assert p1 - p0 == n - 1
+
+    gathered = {}
+
+    def step():
+        reg.register_async(n)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                gathered["off"] = shard.gather_offsets(dev_off, total_frames)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    launches0 = reg.kernel_launches
+    kt = {"kpe_ms": 0.0, "kpm_ms": 0.0, "declare_ms": 0.0}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        t = reg.kernel_times()  # per-kernel CUDA events of this step (waits for the step's last event)
+        for k in kt:
+            kt[k] += t[k]
+    ev1.record(stream)
+    sync_all()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = reg.kernel_launches - launches0
+    clocks = sampler.stop()
+    t_ms = torch.tensor([dev_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    max_ms = float(t_ms.item())
+    value = total_frames * args.steps / (max_ms * 1e-3)
+
+    # correctness of what was timed: declared offsets == the generator's ground truth
+    off = reg.fetch_offsets(n - 1)
+    ok = bool(((off["flags"] & RB_OFFSET_VALID) != 0).all() and
+              np.array_equal(np.stack([off["dx"], off["dy"]], 1), seq.true_offsets))
+    kp_total = reg.count_keypoints(n)
+    kpf = kp_total / n
+
+    # ---- e2e: host buffers in, host results out, copies inside the timed region -----------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            reg.upload(host_frames)
+            reg.register_async(n)
+            reg.fetch_offsets(n - 1, out=host_off)
+            if world > 1:
+                gathered["off"] = shard.gather_offsets(host_off, total_frames, device=dev)
+
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        esteps = max(2, min(args.steps, 5))
+        for _ in range(esteps):
+            e2e_step()
+        e1.record(stream)
+        sync_all()
+        wall = time.perf_counter() - t0
+        em = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], device=dev)
+        if world > 1:
+            dist.all_reduce(em, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_frames * esteps / float(em.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * args.width * args.height), "d2h_bytes_per_step": int((n - 1) * 12),
+               "steps": esteps, "note": "rb_upload (pinned host frames) + rb_register_async + rb_fetch_offsets per step; "
+                                        "wall clock and CUDA events, the larger of the two, max over ranks"}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        W, H = args.width, args.height
+        # algorithmic bytes: B_alg = 2 W H + 60 K + 12 per frame, of which K1 (kpe)
+        # carries frame read + median write + keypoint write = 2 W H + 20 K, and K2 (kpm) carries the
+        # keypoint reads (as curr and as prev) + result = 40 K + 12.
+        b_path = 2 * W * H + 60 * kpf + 12
+        b_kpe = 2 * W * H + 20 * kpf
+        b_kpm = 40 * kpf + 12
+        kpe_s = kt["kpe_ms"] / args.steps * 1e-3
+        kpm_s = kt["kpm_ms"] / args.steps * 1e-3
+        dominant = "rb_kpe_kernel" if kpe_s >= kpm_s else "rb_kpm_kernel"
+        dom_s = max(kpe_s, kpm_s)
+        dom_bytes = (b_kpe if dominant == "rb_kpe_kernel" else b_kpm) * n
+        achieved = dom_bytes / dom_s / 1e9
+        step_s = max_ms * 1e-3 / args.steps
+        roofline = {
+            "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes,
+            "kernel_ms": {k: v / args.steps for k, v in kt.items()},
+            "kernel_share_of_step": {"kpe": kpe_s / step_s, "kpm": kpm_s / step_s},
+            "path": {"bytes_per_frame": b_path, "achieved": b_path * n / step_s / 1e9,
+                     "frac": b_path * n / step_s / 1e9 / peak},
+            "note": "integer bit-sliced stencil + shared-memory hash join: ALU/LSU-bound, not HBM-bound; "
+                    "see DESIGN.md and profiles/",
+        }
+        cpu = None
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = min(n, max(args.cpu_sample, 64 * threads))
+            r = cpu_reference(seq.frames[:sample], threads)
+            r1 = cpu_reference(seq.frames[: max(sample // threads, 200)], 1)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                   "single_thread_value": r1["value"],
+                   "sample": f"first {sample} frames of rank 0's sequence, one contiguous shard per host thread, "
+                             "kpe::extractor::extract + kpm::match per frame (the reference runs its loop on one thread)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, kpf), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "parity_ok": ok,
+        }
+        print(json.dumps(line), flush=True)
+        if not ok:
+            print("ERROR: declared offsets differ from the generator's ground truth", file=sys.stderr)
+    reg.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
+
+
+if __name__ == "__main__":
+    main()

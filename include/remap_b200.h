@@ -1,0 +1,152 @@
+/* remap_b200.h -- C ABI of the B200-native registration path for kataklinger/remap.
+ *
+ * This is the drop-in boundary.  The reference (header-only C++20, /root/reference/src) has no
+ * plugin or FFI layer; the seam for its per-frame registration hot path is the public surface of
+ * frc::collector (src/frc.hpp:51-80), which mpb::builder::collect names concretely
+ * (src/mpb.hpp:52-61).  include/frc_b200.hpp is a collector-shaped C++ shim over this ABI; the
+ * entry points below are what that shim (or a ctypes / cgo / JNI stub) binds.  INTEGRATION.md shows
+ * the one-line change in mpb.hpp.
+ *
+ * All functions return 0 on success and a negative rb_status on failure; none throws.  The library
+ * has NO host compute path: every result is produced by the sm_100a kernels, and rb_create fails
+ * with RB_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Conventions: caller allocates every buffer; the library never frees caller memory; host pointers
+ * may be pageable or pinned (pinned makes the copies asynchronous); one CUDA stream per context; a
+ * context is not thread-safe; one context per GPU.
+ */
+#ifndef REMAP_B200_H
+#define REMAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_ABI_VERSION 1
+
+typedef enum rb_status {
+  RB_OK = 0,
+  RB_ERR_INVALID = -1,   /* bad argument / configuration                    */
+  RB_ERR_NO_DEVICE = -2, /* no usable CUDA device (there is no CPU fallback) */
+  RB_ERR_CUDA = -3,      /* a CUDA call failed; see rb_last_error            */
+  RB_ERR_CAPACITY = -4,  /* more frames than the context was created for     */
+  RB_ERR_STATE = -5      /* call sequence error (e.g. register before upload) */
+} rb_status;
+
+typedef struct rb_ctx rb_ctx;
+
+/* Replaces the compile-time constants of frc (src/frc.hpp:22-24: grid 4x2, overlap 16;
+ * src/frc.hpp:32-33: weight_switch 10, region_votes 3) and the collector's window dimensions
+ * (src/frc.hpp:51-53).  rb_default_config fills in the reference's values. */
+typedef struct rb_config {
+  uint32_t width, height;   /* frame (action window) size in pixels                       */
+  uint32_t grid_w, grid_h;  /* kpr::grid<4, 2>                                             */
+  uint32_t overlap;         /* frc::grid_overlap                                           */
+  uint32_t weight_switch;   /* match_config::weight_switch                                 */
+  uint32_t region_votes;    /* match_config::region_votes (1..3)                           */
+  int32_t device;           /* CUDA device ordinal                                         */
+  uint32_t max_frames;      /* capacity of the HBM-resident frame store of this context    */
+  uint32_t compute_median;  /* 1: K1 also writes the median image (kpe's second output)    */
+  uint32_t code_slots;      /* 0 = auto; shared-memory code table slots (power of two)     */
+  uint32_t offset_slots;    /* 0 = auto; shared-memory offset table slots (power of two)   */
+  uint32_t profile;         /* 1: record CUDA events around every kernel (rb_kernel_times) */
+  void* stream;             /* cudaStream_t to use, or NULL to create one                  */
+} rb_config;
+
+/* == std::optional<cdt::offset_t> returned by kpm::match (src/kpm.hpp:395-415), plus flags. */
+typedef struct rb_offset {
+  int32_t dx, dy;  /* prev - curr keypoint offset (src/kpm.hpp:96-98)                         */
+  uint32_t flags;  /* RB_OFFSET_VALID: has_value(); RB_OFFSET_TIE_SENSITIVE: see DESIGN.md    */
+} rb_offset;
+#define RB_OFFSET_VALID 1u
+#define RB_OFFSET_TIE_SENSITIVE 2u
+
+/* One keypoint as kpe::extractor hands it to kpr::grid::add (src/kpe.hpp:225-229,301-303):
+ * the 13-byte kpr::code (src/kpr.hpp:20-23, layout src/kpe.hpp:342-379), the point, and the set of
+ * grid regions it is inserted into (bit i = region i, src/kpr.hpp:71-74). */
+typedef struct rb_keypoint {
+  uint8_t code[13];
+  uint8_t weight;
+  uint16_t x, y;
+  uint32_t region_mask;
+} rb_keypoint;
+
+/* One offset-histogram bin of one region: an entry of kpm's totalizator_t (src/kpm.hpp:70-76). */
+typedef struct rb_bin {
+  int32_t dx, dy;
+  uint32_t count;
+} rb_bin;
+
+/* One region's ballot: kpm::details::cast_vote's ticket (src/kpm.hpp:213-223) + tie statistics. */
+typedef struct rb_region_vote {
+  uint32_t use_all;          /* weight switch outcome (src/kpm.hpp:219-220)        */
+  uint32_t n_prev, n_curr;   /* insertions into the region (prev / curr frame)     */
+  uint32_t w2_prev, w2_curr; /* weight-2 insertions                                */
+  uint32_t nbins;            /* distinct offsets                                   */
+  uint32_t nticket;          /* min(region_votes, nbins)                           */
+  rb_bin ticket[4];          /* count desc, dx asc, dy asc                         */
+  uint32_t ngt[4], nge[4];   /* #bins with count > / >= ticket[k].count            */
+} rb_region_vote;
+
+void rb_default_config(rb_config* cfg, uint32_t width, uint32_t height, uint32_t max_frames);
+
+/* frc::collector::collector(dimensions) (src/frc.hpp:51-53): allocates the HBM frame store, the
+ * per-frame keypoint bit maps, the median store and the per-pair ballots. */
+int rb_create(const rb_config* cfg, rb_ctx** out);
+void rb_destroy(rb_ctx* ctx);
+
+/* feed.produce() for n frames at once (src/frc.hpp:86,102; src/ifd.hpp:20-28): frames = n*H*W
+ * bytes, row-major, one C64 colour 0..15 per byte (src/nil.hpp:14-31).  Copies them into the
+ * context's frame store starting at slot `first` (asynchronously on the context's stream). */
+int rb_upload(rb_ctx* ctx, const uint8_t* frames, size_t first, size_t n);
+
+/* The registration of frames [first, first+n): kpe::extractor::extract on every frame
+ * (src/frc.hpp:90,105) and kpm::match on every consecutive pair (src/frc.hpp:107).  Enqueues the
+ * kernels on the context's stream and returns; results stay in HBM until fetched. */
+int rb_register_async(rb_ctx* ctx, size_t first, size_t n);
+
+/* Copies the n-1 pair results of the last rb_register_async to the host and waits for them.
+ * out[i] belongs to frames (first+i, first+i+1). */
+int rb_fetch_offsets(rb_ctx* ctx, rb_offset* out, size_t n_pairs);
+
+/* kpe's median image (src/kpe.hpp:314) of frames [first, first+n): n*H*W bytes. */
+int rb_fetch_medians(rb_ctx* ctx, size_t first, size_t n, uint8_t* out);
+
+/* rb_register_async + rb_fetch_offsets (+ rb_fetch_medians when out_median != NULL). */
+int rb_register(rb_ctx* ctx, size_t first, size_t n, rb_offset* out, uint8_t* out_median);
+
+/* Parity taps (not on the hot path). */
+int rb_keypoints(rb_ctx* ctx, size_t frame, rb_keypoint* out, size_t cap, size_t* count);
+int rb_region_ballots(rb_ctx* ctx, size_t pair, rb_region_vote* out /* grid_w*grid_h entries */);
+int rb_region_votes(rb_ctx* ctx, size_t pair, uint32_t region, rb_bin* out, size_t cap, size_t* count);
+
+/* fde::details::generate_mask (src/fde.hpp:19-55): mask[y][x] = 0xFF where the background map
+ * equals the frame placed at (px, py), else 0.  bg = bgH*bgW bytes, frame/out_mask = H*W bytes. */
+int rb_foreground_mask(rb_ctx* ctx, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, int32_t py,
+                       const uint8_t* frame, uint8_t* out_mask);
+/* Same, frame taken from the resident frame store; mask left in HBM unless out_mask != NULL. */
+int rb_foreground_mask_resident(rb_ctx* ctx, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px,
+                                int32_t py, size_t frame, uint8_t* out_mask);
+
+/* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
+ * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */
+const rb_offset* rb_offsets_device(rb_ctx* ctx);
+/* Number of keypoints (unique pixels, not region insertions) K1 found in frames [first, first+n). */
+int rb_count_keypoints(rb_ctx* ctx, size_t first, size_t n, uint64_t* total);
+
+/* Introspection for benchmarks and tests. */
+int rb_synchronize(rb_ctx* ctx);
+void* rb_stream(rb_ctx* ctx);                          /* the cudaStream_t the kernels run on       */
+int rb_kernel_times(rb_ctx* ctx, float* ms, size_t n); /* last rb_register_async: kpe, kpm, declare */
+uint64_t rb_kernel_launches(rb_ctx* ctx);              /* kernels launched by this context so far   */
+size_t rb_device_bytes(rb_ctx* ctx);                   /* HBM held by this context                  */
+const char* rb_last_error(rb_ctx* ctx);
+uint32_t rb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REMAP_B200_H */

@@ -1,0 +1,180 @@
+"""Thin Python face of the C ABI (include/remap_b200.h): one Registrar per GPU.
+
+All computation happens in libremap_b200.so's sm_100a kernels; this file only marshals numpy
+buffers.  Record layouts (numpy dtypes) mirror the C structs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+OFFSET_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("flags", "<u4")])
+KEYPOINT_DTYPE = np.dtype([("code", "u1", (13,)), ("weight", "u1"), ("x", "<u2"), ("y", "<u2"),
+                           ("region_mask", "<u4")], align=True)
+BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
+VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
+                       ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
+                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,))])
+assert KEYPOINT_DTYPE.itemsize == 24 and OFFSET_DTYPE.itemsize == 12
+
+
+class RemapError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"remap_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Registrar:
+    """Owns one rb_ctx: an HBM-resident frame store plus the registration kernels.
+
+    Mirrors the reference constants by default: grid 4x2, overlap 16 (src/frc.hpp:22-24),
+    weight_switch 10, region_votes 3 (src/frc.hpp:32-33).
+    """
+
+    def __init__(self, width, height, max_frames, device=0, compute_median=True, profile=False, stream=None,
+                 code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3):
+        self._lib = _lib.load()
+        cfg = _lib.RbConfig()
+        self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
+        cfg.grid_w, cfg.grid_h = grid
+        cfg.overlap, cfg.weight_switch, cfg.region_votes = overlap, weight_switch, region_votes
+        cfg.device = device
+        cfg.compute_median = int(bool(compute_median))
+        cfg.profile = int(bool(profile))
+        cfg.code_slots, cfg.offset_slots = code_slots, offset_slots
+        cfg.stream = stream
+        self.width, self.height, self.max_frames = width, height, max_frames
+        self.nreg = grid[0] * grid[1]
+        self._ctx = C.c_void_p()
+        rc = self._lib.rb_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.rb_last_error(self._ctx).decode() if self._ctx else "no CUDA device (no CPU fallback exists)"
+            if self._ctx:
+                self._lib.rb_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise RemapError(rc, msg)
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RemapError(rc, self._lib.rb_last_error(self._ctx).decode())
+
+    # -- the path ---------------------------------------------------------------------------
+    def upload(self, frames, first=0):
+        """frames: (n, H, W) uint8, values 0..15 (nil::read_raw format)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width), frames.shape
+        self._check(self._lib.rb_upload(self._ctx, frames.ctypes.data_as(C.c_void_p), first, frames.shape[0]))
+        self._keep = frames  # the copy is asynchronous for pinned memory
+
+    def upload_ptr(self, ptr, n, first=0):
+        self._check(self._lib.rb_upload(self._ctx, C.c_void_p(ptr), first, n))
+
+    def register_async(self, n, first=0):
+        self._check(self._lib.rb_register_async(self._ctx, first, n))
+
+    def fetch_offsets(self, n_pairs, out=None):
+        if out is None:
+            out = np.zeros(n_pairs, OFFSET_DTYPE)
+        self._check(self._lib.rb_fetch_offsets(self._ctx, out.ctypes.data_as(C.c_void_p), n_pairs))
+        return out
+
+    def fetch_medians(self, n, first=0):
+        out = np.zeros((n, self.height, self.width), np.uint8)
+        self._check(self._lib.rb_fetch_medians(self._ctx, first, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def register(self, n, first=0, want_medians=False):
+        """-> (offsets (n-1,) OFFSET_DTYPE, medians (n, H, W) or None)"""
+        self.register_async(n, first)
+        off = self.fetch_offsets(n - 1)
+        return off, (self.fetch_medians(n, first) if want_medians else None)
+
+    def synchronize(self):
+        self._check(self._lib.rb_synchronize(self._ctx))
+
+    # -- taps ---------------------------------------------------------------------------------
+    def keypoints(self, frame):
+        cap = self.width * self.height
+        out = np.zeros(cap, KEYPOINT_DTYPE)
+        n = C.c_size_t()
+        self._check(self._lib.rb_keypoints(self._ctx, frame, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def region_ballots(self, pair):
+        out = np.zeros(self.nreg, VOTE_DTYPE)
+        self._check(self._lib.rb_region_ballots(self._ctx, pair, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def region_votes(self, pair, region):
+        cap = 1 << 20
+        out = np.zeros(cap, BIN_DTYPE)
+        n = C.c_size_t()
+        self._check(self._lib.rb_region_votes(self._ctx, pair, region, out.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        b = out[:n.value]
+        return b[np.lexsort((b["dy"], b["dx"]))].copy()
+
+    def foreground_mask(self, bg, px, py, frame):
+        bg = np.ascontiguousarray(bg, np.uint8)
+        frame = np.ascontiguousarray(frame, np.uint8)
+        assert frame.shape == (self.height, self.width)
+        out = np.zeros_like(frame)
+        self._check(self._lib.rb_foreground_mask(self._ctx, bg.ctypes.data_as(C.c_void_p), bg.shape[1], bg.shape[0],
+                                                 px, py, frame.ctypes.data_as(C.c_void_p),
+                                                 out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def foreground_mask_resident(self, bg, px, py, frame_index):
+        bg = np.ascontiguousarray(bg, np.uint8)
+        out = np.zeros((self.height, self.width), np.uint8)
+        self._check(self._lib.rb_foreground_mask_resident(self._ctx, bg.ctypes.data_as(C.c_void_p), bg.shape[1],
+                                                          bg.shape[0], px, py, frame_index,
+                                                          out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- introspection ------------------------------------------------------------------------
+    @property
+    def stream(self):
+        return self._lib.rb_stream(self._ctx)
+
+    def kernel_times(self):
+        ms = (C.c_float * 3)()
+        self._check(self._lib.rb_kernel_times(self._ctx, ms, 3))
+        return dict(kpe_ms=ms[0], kpm_ms=ms[1], declare_ms=ms[2])
+
+    @property
+    def offsets_device_ptr(self):
+        return self._lib.rb_offsets_device(self._ctx)
+
+    def count_keypoints(self, n, first=0):
+        t = C.c_uint64()
+        self._check(self._lib.rb_count_keypoints(self._ctx, first, n, C.byref(t)))
+        return int(t.value)
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.rb_kernel_launches(self._ctx))
+
+    @property
+    def device_bytes(self):
+        return int(self._lib.rb_device_bytes(self._ctx))

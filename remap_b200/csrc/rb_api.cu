@@ -1,0 +1,583 @@
+// rb_api.cu -- libremap_b200.so: the C ABI of include/remap_b200.h over the sm_100a kernels.
+//
+// No host compute path exists in this library: every result comes out of a kernel below.  The only
+// host work is geometry set-up, launches and copies.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/remap_b200.h"
+#include "rb_host.hpp"
+#include "rb_kpe.cuh"
+#include "rb_kpm.cuh"
+
+static_assert(sizeof(rb_region_vote) == sizeof(RbRegionVote), "ABI mirror of RbRegionVote");
+static_assert(sizeof(rb_bin) == sizeof(RbBin), "ABI mirror of RbBin");
+static_assert(sizeof(rb_keypoint) == 24, "rb_keypoint layout");
+static_assert(sizeof(rb_offset) == 12, "rb_offset layout");
+
+// ---- small kernels ------------------------------------------------------------------------------
+
+// K3 wrapper: also emits the compact rb_offset the caller fetches.
+__global__ void rb_declare_offsets_kernel(const RbGeom g, const RbRegionVote* votes, RbPairResult* results,
+                                          rb_offset* offsets, uint32_t npairs) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  RbPairResult r;
+  rbm::declare_pair(g, votes + (uint64_t)i * g.nreg, &r);
+  results[i] = r;
+  rb_offset o;
+  o.dx = r.dx;
+  o.dy = r.dy;
+  o.flags = (r.valid ? RB_OFFSET_VALID : 0u) | (r.tie_sensitive ? RB_OFFSET_TIE_SENSITIVE : 0u);
+  offsets[i] = o;
+}
+
+// Parity tap: expands K1's bit maps of one frame into rb_keypoint records in the reference's
+// insertion order (column-major: x outer, y inner; src/kpe.hpp:201-204,289-305), with the 13-byte
+// code laid out exactly as kpe::extractor::encode_keypoint does (src/kpe.hpp:342-379).
+__global__ void rb_keypoints_kernel(const RbGeom g, const uint8_t* frame, const uint32_t* kpbits,
+                                    const uint32_t* w2bits, rb_keypoint* out, uint32_t cap, uint32_t* count) {
+  extern __shared__ uint32_t colstart[];  // [W + 1]
+  const uint32_t W = g.W, H = g.H;
+  for (uint32_t x = threadIdx.x; x < W; x += blockDim.x) {
+    uint32_t n = 0;
+    if (x >= 2 && x + 2 < W) {
+      const uint32_t j = (x - 2) / RB_STRIP_OUT, b = x - RB_STRIP_OUT * j;
+      for (uint32_t y = 2; y + 4 < H; ++y) n += (kpbits[(uint64_t)y * g.NS + j] >> b) & 1u;
+    }
+    colstart[x + 1] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    colstart[0] = 0;
+    for (uint32_t x = 0; x < W; ++x) colstart[x + 1] += colstart[x];
+    *count = colstart[W];
+  }
+  __syncthreads();
+  for (uint32_t x = threadIdx.x; x < W; x += blockDim.x) {
+    if (x < 2 || x + 2 >= W) continue;
+    const uint32_t j = (x - 2) / RB_STRIP_OUT, b = x - RB_STRIP_OUT * j;
+    uint32_t at = colstart[x];
+    uint32_t colbits = 0;
+    for (uint32_t s = 0; s < g.grid_w; ++s)
+      if (x >= g.col0[s] && x < g.col1[s]) colbits |= 1u << s;
+    for (uint32_t y = 2; y + 4 < H; ++y) {
+      if (!((kpbits[(uint64_t)y * g.NS + j] >> b) & 1u)) continue;
+      if (at < cap) {
+        const uint32_t weight = ((w2bits[(uint64_t)y * g.NS + j] >> b) & 1u) ? 2u : 1u;
+        uint8_t v[5][5];
+        for (int r = 0; r < 5; ++r)
+          for (int c = 0; c < 5; ++c) v[r][c] = frame[(uint64_t)(y - 2 + r) * g.pitch + (x - 2 + c)] & 15;
+        rb_keypoint k;
+        k.code[0] = v[0][0] | (v[0][1] << 4);  k.code[1] = v[0][2] | (v[0][3] << 4);
+        k.code[2] = v[1][0] | (v[0][4] << 4);  k.code[3] = v[1][1] | (v[1][2] << 4);
+        k.code[4] = v[1][3] | (v[1][4] << 4);  k.code[5] = v[2][0] | (v[2][1] << 4);
+        k.code[6] = v[2][2] | (v[2][3] << 4);  k.code[7] = v[3][0] | (v[2][4] << 4);
+        k.code[8] = v[3][1] | (v[3][2] << 4);  k.code[9] = v[3][3] | (v[3][4] << 4);
+        k.code[10] = v[4][0] | (v[4][1] << 4); k.code[11] = v[4][2] | (v[4][3] << 4);
+        k.code[12] = weight | (v[4][4] << 4);
+        k.weight = (uint8_t)weight;
+        k.x = (uint16_t)x;
+        k.y = (uint16_t)y;
+        uint32_t mask = 0;  // region idx = grid_h * colsect + rowsect (src/kpr.hpp:71-74)
+        for (uint32_t a = 0; a < g.grid_w; ++a)
+          if (colbits & (1u << a))
+            for (uint32_t bb = 0; bb < g.grid_h; ++bb)
+              if (y >= g.row0[bb] && y < g.row1[bb]) mask |= 1u << (g.grid_h * a + bb);
+        k.region_mask = mask;
+        out[at] = k;
+      }
+      ++at;
+    }
+  }
+}
+
+// fde::details::generate_mask (src/fde.hpp:19-55): byte-wise equality of the frame with the
+// background window at linear offset idx, 0xFF where equal.  16 pixels per thread: one 128-bit
+// frame load, five 32-bit background loads funnel-shifted to the frame's alignment, one 128-bit
+// store; scalar tail.  HBM-bound: 2 bytes read + 1 byte written per pixel.
+__global__ void rb_fgmask_kernel(const uint8_t* __restrict__ bg, long long idx, uint32_t bgW,
+                                 const uint8_t* __restrict__ frame, uint32_t fpitch, uint8_t* __restrict__ mask,
+                                 uint32_t mpitch, uint32_t W, uint32_t H) {
+  const uint32_t chunks = (W + 15) / 16;
+  const uint32_t total = chunks * H;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t y = i / chunks, x = (i % chunks) * 16;
+    const uint8_t* f = frame + (uint64_t)y * fpitch + x;
+    const uint8_t* b = bg + idx + (long long)y * bgW + x;
+    uint8_t* m = mask + (uint64_t)y * mpitch + x;
+    const bool vec = x + 16 <= W && ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(m)) & 15) == 0;
+    if (vec) {
+      const uint4 fv = __ldg(reinterpret_cast<const uint4*>(f));
+      const uintptr_t ba = reinterpret_cast<uintptr_t>(b);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(ba & ~(uintptr_t)3);
+      const uint32_t sh = (uint32_t)(ba & 3) * 8;
+      const uint32_t w0 = __ldg(bw), w1 = __ldg(bw + 1), w2 = __ldg(bw + 2), w3 = __ldg(bw + 3);
+      const uint32_t w4 = sh ? __ldg(bw + 4) : 0u;
+      uint4 o;
+      o.x = __vcmpeq4(__funnelshift_r(w0, w1, sh), fv.x);
+      o.y = __vcmpeq4(__funnelshift_r(w1, w2, sh), fv.y);
+      o.z = __vcmpeq4(__funnelshift_r(w2, w3, sh), fv.z);
+      o.w = __vcmpeq4(__funnelshift_r(w3, w4, sh), fv.w);
+      *reinterpret_cast<uint4*>(m) = o;
+    } else {
+      for (uint32_t k = 0; k < 16 && x + k < W; ++k) m[k] = b[k] == f[k] ? 0xFF : 0x00;
+    }
+  }
+}
+
+// popcount of K1's keypoint bit maps (statistics for the roofline's K term)
+__global__ void rb_count_kernel(const uint32_t* __restrict__ bits, size_t nwords, unsigned long long* total) {
+  unsigned long long loc = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x)
+    loc += __popc(__ldg(bits + i));
+  for (int o = 16; o > 0; o >>= 1) loc += __shfl_down_sync(0xffffffffu, loc, o);
+  if ((threadIdx.x & 31) == 0 && loc) atomicAdd(total, loc);
+}
+
+// ---- context ------------------------------------------------------------------------------------
+
+struct rb_ctx {
+  rb_config cfg;
+  RbGeom g;
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  bool own_stream;
+  uint8_t* d_frames;
+  uint8_t* d_median;
+  uint32_t* d_kp;
+  uint32_t* d_w2;
+  RbRegionVote* d_votes;
+  RbPairResult* d_results;
+  rb_offset* d_offsets;
+  RbBin* d_tap_bins;
+  uint32_t* d_tap_count;
+  rb_keypoint* d_kps;
+  uint8_t* d_bg;       // scratch for rb_foreground_mask
+  size_t bg_cap;
+  uint8_t* d_fgframe;  // dense frame scratch
+  uint8_t* d_mask;     // dense mask [H][W]
+  size_t bytes;
+  uint32_t code_slots, off_slots, tile_pitch, tile_rows;
+  size_t kpm_smem;
+  size_t uploaded;       // frames [0, uploaded) hold data
+  size_t reg_first, reg_n;
+  cudaEvent_t ev[4];
+  uint64_t launches;
+  std::string err;
+};
+
+#define RB_CUDA(ctx, call)                                                                      \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      return RB_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+static uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <typename T>
+static cudaError_t dmalloc(rb_ctx* c, T** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+  if (e == cudaSuccess) c->bytes += bytes;
+  return e;
+}
+
+extern "C" {
+
+uint32_t rb_abi_version(void) { return RB_ABI_VERSION; }
+
+void rb_default_config(rb_config* cfg, uint32_t width, uint32_t height, uint32_t max_frames) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->width = width;
+  cfg->height = height;
+  cfg->grid_w = 4;          // src/frc.hpp:22
+  cfg->grid_h = 2;          // src/frc.hpp:23
+  cfg->overlap = 16;        // src/frc.hpp:24
+  cfg->weight_switch = 10;  // src/frc.hpp:32
+  cfg->region_votes = 3;    // src/frc.hpp:33
+  cfg->device = 0;
+  cfg->max_frames = max_frames;
+  cfg->compute_median = 1;
+}
+
+int rb_create(const rb_config* cfg, rb_ctx** out) {
+  if (!cfg || !out) return RB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    cudaGetLastError();
+    return RB_ERR_NO_DEVICE;  // there is deliberately no CPU fallback
+  }
+  rb_ctx* c = new (std::nothrow) rb_ctx();
+  if (!c) return RB_ERR_INVALID;
+  c->cfg = *cfg;
+  c->device = cfg->device;
+  *out = c;  // returned even on failure so that rb_last_error can be read; caller rb_destroy()s it
+  if (cfg->max_frames < 2) { c->err = "max_frames must be >= 2"; return RB_ERR_INVALID; }
+  if (rb_make_geom(cfg->width, cfg->height, cfg->grid_w, cfg->grid_h, cfg->overlap, cfg->weight_switch,
+                   cfg->region_votes, &c->g) != 0) {
+    c->err = "unsupported frame size / grid (need W/grid_w > overlap/2, H/grid_h > overlap/2, grid <= 8x8, W,H < 32768)";
+    return RB_ERR_INVALID;
+  }
+  if (cfg->width >= 32768 || cfg->height >= 32768) { c->err = "frame too large"; return RB_ERR_INVALID; }
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  if (cfg->stream) { c->stream = static_cast<cudaStream_t>(cfg->stream); c->own_stream = false; }
+  else { RB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  for (int i = 0; i < 4; ++i) RB_CUDA(c, cudaEventCreate(&c->ev[i]));
+
+  // K2 shared-memory budget
+  uint32_t maxw = 0, maxh = 0, maxcols = 0;
+  for (uint32_t s = 0; s < g.grid_w; ++s) {
+    const uint32_t tx0 = (g.col0[s] - 2) & ~7u, tw = (g.col1[s] + 2 - tx0 + 7) / 8;
+    if (tw > maxw) maxw = tw;
+    if (g.col1[s] - g.col0[s] > maxcols) maxcols = g.col1[s] - g.col0[s];
+  }
+  for (uint32_t s = 0; s < g.grid_h; ++s)
+    if (g.row1[s] - g.row0[s] > maxh) maxh = g.row1[s] - g.row0[s];
+  c->tile_pitch = maxw + 1;
+  c->tile_rows = maxh + 4;
+  const uint32_t area = maxcols * maxh;
+  c->code_slots = cfg->code_slots ? cfg->code_slots : next_pow2(area / 4 < 1024 ? 1024 : area / 4);
+  c->off_slots = cfg->offset_slots ? cfg->offset_slots : 1024;
+  if (c->code_slots > 16384 && !cfg->code_slots) c->code_slots = 16384;
+  if ((c->code_slots & (c->code_slots - 1)) || (c->off_slots & (c->off_slots - 1)) || c->code_slots < 64 ||
+      c->code_slots / 2 < maxcols || c->off_slots <= 2 * 256) {
+    c->err = "code_slots / offset_slots must be powers of two, code_slots/2 >= region width, offset_slots > 512";
+    return RB_ERR_INVALID;
+  }
+  int smem_max = 0;
+  RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  for (;;) {
+    RbKpmParams p;
+    memset(&p, 0, sizeof(p));
+    p.code_slots = c->code_slots; p.off_slots = c->off_slots; p.tile_pitch = c->tile_pitch; p.tile_rows = c->tile_rows;
+    c->kpm_smem = rbm::smem_words(p, 256) * sizeof(uint32_t);
+    if (c->kpm_smem <= (size_t)smem_max) break;
+    if (!cfg->code_slots && c->code_slots / 2 >= 2 * maxcols && c->code_slots > 1024) { c->code_slots /= 2; continue; }
+    c->err = "region tiles + hash tables exceed the shared memory of one CTA";
+    return RB_ERR_INVALID;
+  }
+  RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kpm_smem));
+
+  const size_t N = cfg->max_frames;
+  RB_CUDA(c, dmalloc(c, &c->d_frames, g.frame_stride * N + 256));
+  RB_CUDA(c, dmalloc(c, &c->d_kp, (size_t)N * g.H * g.NS * 4));
+  RB_CUDA(c, dmalloc(c, &c->d_w2, (size_t)N * g.H * g.NS * 4));
+  RB_CUDA(c, dmalloc(c, &c->d_votes, (size_t)N * g.nreg * sizeof(RbRegionVote)));
+  RB_CUDA(c, dmalloc(c, &c->d_results, (size_t)N * sizeof(RbPairResult)));
+  RB_CUDA(c, dmalloc(c, &c->d_offsets, (size_t)N * sizeof(rb_offset)));
+  RB_CUDA(c, dmalloc(c, &c->d_tap_bins, ((size_t)1 << 20) * sizeof(RbBin)));
+  RB_CUDA(c, dmalloc(c, &c->d_tap_count, 256));
+  RB_CUDA(c, dmalloc(c, &c->d_kps, (size_t)g.W * g.H * sizeof(rb_keypoint)));
+  RB_CUDA(c, dmalloc(c, &c->d_fgframe, (size_t)g.W * g.H + 256));
+  RB_CUDA(c, dmalloc(c, &c->d_mask, (size_t)g.W * g.H + 256));
+  RB_CUDA(c, cudaMemsetAsync(c->d_frames, 0, g.frame_stride * N + 256, c->stream));
+  RB_CUDA(c, cudaMemsetAsync(c->d_kp, 0, (size_t)N * g.H * g.NS * 4, c->stream));
+  RB_CUDA(c, cudaMemsetAsync(c->d_w2, 0, (size_t)N * g.H * g.NS * 4, c->stream));
+  if (cfg->compute_median) {
+    RB_CUDA(c, dmalloc(c, &c->d_median, g.median_stride * N + 256));
+    // rows/columns outside the keypoint domain are never written and must read 0 (src/frc.hpp:104)
+    RB_CUDA(c, cudaMemsetAsync(c->d_median, 0, g.median_stride * N + 256, c->stream));
+  }
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+void rb_destroy(rb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
+  cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
+  cudaFree(c->d_kps); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
+  for (int i = 0; i < 4; ++i)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* rb_last_error(rb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+const rb_offset* rb_offsets_device(rb_ctx* c) { return c ? c->d_offsets : nullptr; }
+
+int rb_count_keypoints(rb_ctx* c, size_t first, size_t n, uint64_t* total) {
+  if (!c || !total) return RB_ERR_INVALID;
+  if (first + n > c->cfg.max_frames) return RB_ERR_CAPACITY;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(c->d_tap_count + 2);  // 8-byte aligned scratch
+  RB_CUDA(c, cudaMemsetAsync(d, 0, 8, c->stream));
+  const size_t nwords = n * c->g.H * c->g.NS;
+  rb_count_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_kp + first * c->g.H * c->g.NS, nwords, d);
+  ++c->launches;
+  RB_CUDA(c, cudaGetLastError());
+  unsigned long long h = 0;
+  RB_CUDA(c, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *total = h;
+  return RB_OK;
+}
+void* rb_stream(rb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+uint64_t rb_kernel_launches(rb_ctx* c) { return c ? c->launches : 0; }
+size_t rb_device_bytes(rb_ctx* c) { return c ? c->bytes : 0; }
+
+int rb_synchronize(rb_ctx* c) {
+  if (!c) return RB_ERR_INVALID;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+int rb_upload(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
+  if (!c || !frames) return RB_ERR_INVALID;
+  if (first + n > c->cfg.max_frames) { c->err = "rb_upload: beyond max_frames"; return RB_ERR_CAPACITY; }
+  if (n == 0) return RB_OK;
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  uint8_t* dst = c->d_frames + g.frame_stride * first;
+  if (g.pitch == g.W)
+    RB_CUDA(c, cudaMemcpyAsync(dst, frames, (size_t)g.W * g.H * n, cudaMemcpyHostToDevice, c->stream));
+  else
+    RB_CUDA(c, cudaMemcpy2DAsync(dst, g.pitch, frames, g.W, g.W, (size_t)g.H * n, cudaMemcpyHostToDevice, c->stream));
+  if (first + n > c->uploaded) c->uploaded = first + n;
+  return RB_OK;
+}
+
+// Picks the number of row segments per strip: enough CTAs for a few waves on every SM without
+// paying too many 4-row warm-ups.
+static uint32_t pick_segments(const rb_ctx* c, size_t n) {
+  const RbGeom& g = c->g;
+  const uint32_t rows = g.H - 6;
+  const double slots = (double)c->sm_count * 4 /*CTAs of 128 threads per SM at 128 regs*/ * 128;
+  uint32_t best = 1;
+  double best_eff = 0;
+  for (uint32_t s = 1; s <= 32 && rows / s >= 8; ++s) {
+    const double items = (double)n * g.NS * s;
+    const double waves = items / slots;
+    const double eff = waves / (double)(size_t)(waves + 0.999999) * (double)rows / (rows + 4.0 * s);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+  }
+  return best;
+}
+
+int rb_register_async(rb_ctx* c, size_t first, size_t n) {
+  if (!c) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register: frame range"; return RB_ERR_CAPACITY; }
+  if (first + n > c->uploaded) { c->err = "rb_register: frames not uploaded"; return RB_ERR_STATE; }
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const bool prof = c->cfg.profile != 0;
+  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  {
+    RbKpeParams p;
+    p.g = g;
+    p.frames = c->d_frames + g.frame_stride * first;
+    p.median = c->d_median ? c->d_median + g.median_stride * first : nullptr;
+    p.kpbits = c->d_kp + (size_t)first * g.H * g.NS;
+    p.w2bits = c->d_w2 + (size_t)first * g.H * g.NS;
+    p.nframes = (uint32_t)n;
+    p.nseg = pick_segments(c, n);
+    p.seg_rows = (g.H - 6 + p.nseg - 1) / p.nseg;
+    const size_t items = n * p.nseg * g.NS;
+    const uint32_t blocks = (uint32_t)((items + 127) / 128);
+    rb_kpe_kernel<<<blocks, 128, 0, c->stream>>>(p);
+    ++c->launches;
+    RB_CUDA(c, cudaGetLastError());
+  }
+  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  if (n >= 2) {
+    RbKpmParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g;
+    p.frames = c->d_frames;
+    p.kpbits = c->d_kp;
+    p.w2bits = c->d_w2;
+    p.votes = c->d_votes;
+    p.first_frame = (uint32_t)first;
+    p.npairs = (uint32_t)(n - 1);
+    p.code_slots = c->code_slots; p.off_slots = c->off_slots; p.tile_pitch = c->tile_pitch; p.tile_rows = c->tile_rows;
+    rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
+    ++c->launches;
+    RB_CUDA(c, cudaGetLastError());
+    if (prof) RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, c->d_votes, c->d_results,
+                                                                                   c->d_offsets, (uint32_t)(n - 1));
+    ++c->launches;
+    RB_CUDA(c, cudaGetLastError());
+  } else if (prof) {
+    RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+  }
+  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  c->reg_first = first;
+  c->reg_n = n;
+  return RB_OK;
+}
+
+int rb_kernel_times(rb_ctx* c, float* ms, size_t n) {
+  if (!c || !ms || n < 3) return RB_ERR_INVALID;
+  if (!c->cfg.profile) { c->err = "context created without profile=1"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaEventSynchronize(c->ev[3]));
+  for (int i = 0; i < 3; ++i) RB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  return RB_OK;
+}
+
+int rb_fetch_offsets(rb_ctx* c, rb_offset* out, size_t n_pairs) {
+  if (!c || (!out && n_pairs)) return RB_ERR_INVALID;
+  if (c->reg_n == 0 || n_pairs > c->reg_n - 1) { c->err = "rb_fetch_offsets: nothing registered"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  if (n_pairs)
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_offsets, n_pairs * sizeof(rb_offset), cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+int rb_fetch_medians(rb_ctx* c, size_t first, size_t n, uint8_t* out) {
+  if (!c || !out) return RB_ERR_INVALID;
+  if (!c->d_median) { c->err = "context created with compute_median = 0"; return RB_ERR_STATE; }
+  if (first + n > c->cfg.max_frames) return RB_ERR_CAPACITY;
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  // pixel x lives at byte x + 2 of a median row
+  RB_CUDA(c, cudaMemcpy2DAsync(out, g.W, c->d_median + g.median_stride * first + 2, g.mpitch, g.W, (size_t)g.H * n,
+                               cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+int rb_register(rb_ctx* c, size_t first, size_t n, rb_offset* out, uint8_t* out_median) {
+  int rc = rb_register_async(c, first, n);
+  if (rc != RB_OK) return rc;
+  rc = rb_fetch_offsets(c, out, n - 1);
+  if (rc != RB_OK) return rc;
+  if (out_median) rc = rb_fetch_medians(c, first, n, out_median);
+  return rc;
+}
+
+int rb_keypoints(rb_ctx* c, size_t frame, rb_keypoint* out, size_t cap, size_t* count) {
+  if (!c || !count) return RB_ERR_INVALID;
+  if (frame < c->reg_first || frame >= c->reg_first + c->reg_n) {
+    c->err = "rb_keypoints: frame not in the last registered range";
+    return RB_ERR_STATE;
+  }
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t dcap = g.W * g.H;
+  rb_keypoints_kernel<<<1, 1024, (g.W + 1) * sizeof(uint32_t), c->stream>>>(
+      g, c->d_frames + g.frame_stride * frame, c->d_kp + frame * g.H * g.NS, c->d_w2 + frame * g.H * g.NS, c->d_kps,
+      dcap, c->d_tap_count);
+  ++c->launches;
+  RB_CUDA(c, cudaGetLastError());
+  uint32_t n = 0;
+  RB_CUDA(c, cudaMemcpyAsync(&n, c->d_tap_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *count = n;
+  const size_t m = n < cap ? n : cap;
+  if (m && out) {
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_kps, m * sizeof(rb_keypoint), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return RB_OK;
+}
+
+int rb_region_ballots(rb_ctx* c, size_t pair, rb_region_vote* out) {
+  if (!c || !out) return RB_ERR_INVALID;
+  if (c->reg_n < 2 || pair >= c->reg_n - 1) { c->err = "rb_region_ballots: pair not registered"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaMemcpyAsync(out, c->d_votes + pair * c->g.nreg, c->g.nreg * sizeof(RbRegionVote),
+                             cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+// Re-runs the production K2 kernel on one (pair, region) with the bin dump enabled.
+int rb_region_votes(rb_ctx* c, size_t pair, uint32_t region, rb_bin* out, size_t cap, size_t* count) {
+  if (!c || !count) return RB_ERR_INVALID;
+  if (c->reg_n < 2 || pair >= c->reg_n - 1 || region >= c->g.nreg) { c->err = "rb_region_votes: pair/region"; return RB_ERR_STATE; }
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaMemsetAsync(c->d_tap_count, 0, 4, c->stream));
+  RbKpmParams p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.frames = c->d_frames; p.kpbits = c->d_kp; p.w2bits = c->d_w2;
+  p.votes = c->d_votes + (size_t)c->cfg.max_frames * g.nreg - g.nreg;  // scratch slot: last pair row is never used
+  p.first_frame = (uint32_t)(c->reg_first + pair);
+  p.npairs = 1;
+  p.code_slots = c->code_slots; p.off_slots = c->off_slots; p.tile_pitch = c->tile_pitch; p.tile_rows = c->tile_rows;
+  p.tap_bins = c->d_tap_bins; p.tap_cap = 1u << 20; p.tap_count = c->d_tap_count;
+  p.tap_pair = 0; p.tap_region = region;
+  // launch all regions of the pair (blockIdx -> region), only `region` dumps
+  rb_kpm_kernel<<<g.nreg, 256, c->kpm_smem, c->stream>>>(p);
+  ++c->launches;
+  RB_CUDA(c, cudaGetLastError());
+  uint32_t n = 0;
+  RB_CUDA(c, cudaMemcpyAsync(&n, c->d_tap_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *count = n;
+  const size_t m = n < cap ? n : cap;
+  if (m && out) {
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_tap_bins, m * sizeof(rb_bin), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return RB_OK;
+}
+
+static int fgmask_common(rb_ctx* c, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, int32_t py,
+                         const uint8_t* dframe, uint32_t fpitch, uint8_t* out_mask) {
+  const RbGeom& g = c->g;
+  if (px < 0 || py < 0 || (uint64_t)px + g.W > bgW || (uint64_t)py + g.H > bgH) {
+    c->err = "rb_foreground_mask: frame window outside the background";
+    return RB_ERR_INVALID;
+  }
+  const size_t need = (size_t)bgW * bgH + 64;
+  if (need > c->bg_cap) {
+    if (c->d_bg) { cudaFree(c->d_bg); c->bytes -= c->bg_cap; c->d_bg = nullptr; c->bg_cap = 0; }
+    RB_CUDA(c, dmalloc(c, &c->d_bg, need));
+    c->bg_cap = need;
+  }
+  RB_CUDA(c, cudaMemcpyAsync(c->d_bg, bg, (size_t)bgW * bgH, cudaMemcpyHostToDevice, c->stream));
+  const long long idx = (long long)bgW * py + px;  // cdt::to_index (src/cdt.hpp:173-177; src/fde.hpp:87)
+  const uint32_t total = ((g.W + 15) / 16) * g.H;
+  uint32_t blocks = (total + 255) / 256;
+  const uint32_t cap = (uint32_t)c->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  rb_fgmask_kernel<<<blocks, 256, 0, c->stream>>>(c->d_bg, idx, bgW, dframe, fpitch, c->d_mask, g.W, g.W, g.H);
+  ++c->launches;
+  RB_CUDA(c, cudaGetLastError());
+  if (out_mask)
+    RB_CUDA(c, cudaMemcpyAsync(out_mask, c->d_mask, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+int rb_foreground_mask(rb_ctx* c, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, int32_t py,
+                       const uint8_t* frame, uint8_t* out_mask) {
+  if (!c || !bg || !frame || !out_mask) return RB_ERR_INVALID;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RB_CUDA(c, cudaMemcpyAsync(c->d_fgframe, frame, (size_t)c->g.W * c->g.H, cudaMemcpyHostToDevice, c->stream));
+  return fgmask_common(c, bg, bgW, bgH, px, py, c->d_fgframe, c->g.W, out_mask);
+}
+
+int rb_foreground_mask_resident(rb_ctx* c, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, int32_t py,
+                                size_t frame, uint8_t* out_mask) {
+  if (!c || !bg) return RB_ERR_INVALID;
+  if (frame >= c->uploaded) { c->err = "rb_foreground_mask_resident: frame not uploaded"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  return fgmask_common(c, bg, bgW, bgH, px, py, c->d_frames + c->g.frame_stride * frame, c->g.pitch, out_mask);
+}
+
+}  // extern "C"

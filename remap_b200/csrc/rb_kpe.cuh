@@ -1,0 +1,280 @@
+// rb_kpe.cuh -- K1: keypoint extraction (replaces kpe::extractor::extract, src/kpe.hpp:92-108).
+//
+// The reference slides 16-bin byte histograms in AVX2 registers and scans them per pixel
+// (src/kpe.hpp:111-147,207-340).  Here the two rank filters are computed BIT-SLICED: one 32-bit
+// word holds one bit of 32 horizontally adjacent pixels, so a LOP3 works on 32 pixels at once.
+//
+//   p3 = 4th largest of the 3x3 window, p5 = 12th largest of the 5x5 window, in luminance-ordered
+//   space (src/kpe.hpp:313,317,326-340).  For a threshold t in 1..15 let T_t = [ordered >= t] (a
+//   bit plane).  The number of window pixels >= t is a box sum of T_t, and
+//       p3 = #{t : boxsum3x3(T_t) >= 4},   p5 = #{t : boxsum5x5(T_t) >= 12}
+//   because the box sums are monotone in t.  Box sums of bit planes are carry-save adder trees:
+//   vertical 3/5-row sums first (shared between the two filters), then the horizontal sums via
+//   in-register shifts, reduced directly to the ">= k" predicate.
+//
+// Work decomposition: one thread owns one STRIP = a 32-pixel-wide window [28j, 28j+32) of one frame
+// that yields the 28 output columns [28j+2, 28j+30) (2-pixel halo on both sides, so horizontal
+// neighbours are plain shifts and threads never talk to each other), and marches down a segment of
+// rows keeping the threshold planes of the last four rows in registers.  Grid = frames x segments
+// x strips; nothing is shared, so the grid is sized freely in multiples of the SM count.
+//
+// Outputs per frame (fixed size, no atomics, deterministic):
+//   kpbits[y][j]  bit i set <=> pixel (28j + i, y) is a keypoint        (src/kpe.hpp:316-320)
+//   w2bits[y][j]  bit i set <=> that keypoint has weight 2 (p1 != p5)   (src/kpe.hpp:319)
+//   median[y][x]  = ordered_to_native(p3), stored at byte x + 2 of the row (src/kpe.hpp:314)
+// The 13-byte code (src/kpe.hpp:342-379) is a pure function of the 5x5 patch, so it is never
+// materialised in HBM: K2 compares patches directly, and the rb_keypoints tap formats codes on
+// demand.
+#pragma once
+
+#include "rb_common.cuh"
+
+struct RbKpeParams {
+  RbGeom g;
+  const uint8_t* frames;
+  uint8_t* median;    // nullptr: skip
+  uint32_t* kpbits;   // [nframes][H][NS]
+  uint32_t* w2bits;   // [nframes][H][NS]
+  uint32_t nframes;
+  uint32_t nseg;      // row segments per strip
+  uint32_t seg_rows;  // output rows per segment
+};
+
+namespace rbk {
+
+constexpr int N2O[16] = {RB_N2O_LIST};
+constexpr int O2N[16] = {RB_O2N_LIST};
+
+// 8 words of 4 byte-pixels (values 0..15; high nibbles ignored) -> 4 bit planes, bit i of plane k =
+// bit k of pixel i.
+RB_HD void bytes_to_planes(const uint32_t w[8], uint32_t pl[4]) {
+  uint32_t c[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)  // byte b of c[m] = pixel(8m+b) | pixel(8m+4+b) << 4
+    c[m] = (w[2 * m] & 0x0F0F0F0Fu) | ((w[2 * m + 1] << 4) & 0xF0F0F0F0u);
+  // 4x4 byte transpose: d[b] byte m = c[m] byte b, i.e. nibble i of d[b] = pixel 4i + b
+  const uint32_t t0 = rb_prmt(c[0], c[1], 0x5140), t1 = rb_prmt(c[0], c[1], 0x7362);
+  const uint32_t t2 = rb_prmt(c[2], c[3], 0x5140), t3 = rb_prmt(c[2], c[3], 0x7362);
+  uint32_t d0 = rb_prmt(t0, t2, 0x5410), d1 = rb_prmt(t0, t2, 0x7632);
+  uint32_t d2 = rb_prmt(t1, t3, 0x5410), d3 = rb_prmt(t1, t3, 0x7632);
+  // bit address (word b = p1 p0 | nibble p4 p3 p2 | bit k1 k0) -> (word k1 k0 | p4..p0): two rounds of
+  // 2x2 block swaps across words
+  uint32_t t;
+  t = ((d0 >> 1) ^ d1) & 0x55555555u; d1 ^= t; d0 ^= t << 1;
+  t = ((d2 >> 1) ^ d3) & 0x55555555u; d3 ^= t; d2 ^= t << 1;
+  t = ((d0 >> 2) ^ d2) & 0x33333333u; d2 ^= t; d0 ^= t << 2;
+  t = ((d1 >> 2) ^ d3) & 0x33333333u; d3 ^= t; d1 ^= t << 2;
+  pl[0] = d0; pl[1] = d1; pl[2] = d2; pl[3] = d3;
+}
+
+// inverse of bytes_to_planes
+RB_HD void planes_to_bytes(const uint32_t pl[4], uint32_t w[8]) {
+  uint32_t d0 = pl[0], d1 = pl[1], d2 = pl[2], d3 = pl[3], t;
+  t = ((d0 >> 2) ^ d2) & 0x33333333u; d2 ^= t; d0 ^= t << 2;
+  t = ((d1 >> 2) ^ d3) & 0x33333333u; d3 ^= t; d1 ^= t << 2;
+  t = ((d0 >> 1) ^ d1) & 0x55555555u; d1 ^= t; d0 ^= t << 1;
+  t = ((d2 >> 1) ^ d3) & 0x55555555u; d3 ^= t; d2 ^= t << 1;
+  const uint32_t t0 = rb_prmt(d0, d1, 0x5140), t1 = rb_prmt(d0, d1, 0x7362);
+  const uint32_t t2 = rb_prmt(d2, d3, 0x5140), t3 = rb_prmt(d2, d3, 0x7362);
+  uint32_t c[4];
+  c[0] = rb_prmt(t0, t2, 0x5410); c[1] = rb_prmt(t0, t2, 0x7632);
+  c[2] = rb_prmt(t1, t3, 0x5410); c[3] = rb_prmt(t1, t3, 0x7632);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    w[2 * m] = c[m] & 0x0F0F0F0Fu;
+    w[2 * m + 1] = (c[m] >> 4) & 0x0F0F0F0Fu;
+  }
+}
+
+template <int BIT>
+RB_HD uint32_t n2o_plane(const uint32_t n[4]) { return rb_bool4<rb_lut_tt(N2O, BIT)>(n[0], n[1], n[2], n[3]); }
+template <int BIT>
+RB_HD uint32_t o2n_plane(const uint32_t o[4]) { return rb_bool4<rb_lut_tt(O2N, BIT)>(o[0], o[1], o[2], o[3]); }
+
+// T[t-1] = [ordered >= t], t = 1..15, from the four ordered bit planes.
+RB_HD void thresholds(const uint32_t o[4], uint32_t T[15]) {
+  const uint32_t o0 = o[0], o1 = o[1], o2 = o[2], o3 = o[3];
+  T[7] = o3;                    // >= 8
+  T[11] = o3 & o2;              // >= 12
+  T[3] = o3 | o2;               // >= 4
+  T[13] = o3 & o2 & o1;         // >= 14
+  T[9] = o3 & (o2 | o1);        // >= 10
+  T[5] = o3 | (o2 & o1);        // >= 6
+  T[1] = o3 | o2 | o1;          // >= 2
+  T[14] = T[13] & o0;           // >= 15
+  T[12] = T[13] | (T[11] & o0); // >= 13
+  T[10] = T[11] | (T[9] & o0);  // >= 11
+  T[8] = T[9] | (T[7] & o0);    // >= 9
+  T[6] = T[7] | (T[5] & o0);    // >= 7
+  T[4] = T[5] | (T[3] & o0);    // >= 5
+  T[2] = T[3] | (T[1] & o0);    // >= 3
+  T[0] = T[1] | o0;             // >= 1
+}
+
+// One threshold plane, five consecutive rows t4 (y-2) .. t0 (y+2) -> q3 = [3x3 count >= 4],
+// q5 = [5x5 count >= 12] for the 32 pixels of the word (bits 2..29 are exact).
+RB_HD void rank_planes(uint32_t t4, uint32_t t3, uint32_t t2, uint32_t t1, uint32_t t0, uint32_t& q3, uint32_t& q5) {
+  // vertical sums: V3 = t3+t2+t1 = a1 a0 ; V5 = V3 + t4 + t0 = b2 b1 b0
+  const uint32_t a0 = rb_xor3(t3, t2, t1), a1 = rb_maj(t3, t2, t1);
+  const uint32_t b0 = rb_xor3(a0, t4, t0), c = rb_maj(a0, t4, t0);
+  const uint32_t b1 = a1 ^ c, b2 = a1 & c;
+  // 3x3: count = u + 2 v, u = a0(x-1)+a0(x)+a0(x+1), v likewise on a1;  count >= 4 <=> v>=2 | (v>=1 & u>=2)
+  {
+    const uint32_t l0 = a0 << 1, r0 = a0 >> 1, l1 = a1 << 1, r1 = a1 >> 1;
+    q3 = rb_maj(l1, a1, r1) | ((l1 | a1 | r1) & rb_maj(l0, a0, r0));
+  }
+  // 5x5: S = U + 2 V + 4 W with U, V, W the 5-wide horizontal popcounts of b0, b1, b2
+  {
+    // U: only its 2s and 4s bits matter for S >= 12
+    uint32_t e0 = b0 << 2, e1 = b0 << 1, e3 = b0 >> 1, e4 = b0 >> 2;
+    uint32_t s = rb_xor3(e0, e1, b0), k = rb_maj(e0, e1, b0), k2 = rb_maj(s, e3, e4);
+    const uint32_t u1 = k ^ k2, u2 = k & k2;
+    e0 = b1 << 2; e1 = b1 << 1; e3 = b1 >> 1; e4 = b1 >> 2;
+    s = rb_xor3(e0, e1, b1); k = rb_maj(e0, e1, b1);
+    const uint32_t v0 = rb_xor3(s, e3, e4);
+    k2 = rb_maj(s, e3, e4);
+    const uint32_t v1 = k ^ k2, v2 = k & k2;
+    e0 = b2 << 2; e1 = b2 << 1; e3 = b2 >> 1; e4 = b2 >> 2;
+    s = rb_xor3(e0, e1, b2); k = rb_maj(e0, e1, b2);
+    const uint32_t w0 = rb_xor3(s, e3, e4);
+    k2 = rb_maj(s, e3, e4);
+    const uint32_t w1 = k ^ k2, w2 = k & k2;
+    // bit1: u1 + v0 -> carry c1 ; bit2: u2 + v1 + w0 + c1 ; bit3: v2 + w1 + carries ; bit4+: w2 + carries
+    const uint32_t c1 = u1 & v0;
+    const uint32_t x = rb_xor3(u2, v1, w0), cx = rb_maj(u2, v1, w0);
+    const uint32_t s2 = x ^ c1, c2 = x & c1;
+    const uint32_t y = rb_xor3(v2, w1, cx), cy = rb_maj(v2, w1, cx);
+    const uint32_t s3 = y ^ c2, c3 = y & c2;
+    q5 = w2 | cy | c3 | (s3 & s2);  // S >= 16, or 12 <= S <= 15
+  }
+}
+
+// thermometer q[t-1] (t = 1..15, monotone) -> 4 binary planes of p = #{t : q_t}
+RB_HD void thermo_to_binary(const uint32_t q[15], uint32_t p[4]) {
+  p[3] = q[7];
+  p[2] = q[11] | (q[3] & ~q[7]);
+  p[1] = q[13] | (q[9] & ~q[11]) | (q[5] & ~q[7]) | (q[1] & ~q[3]);
+  p[0] = q[14] | (q[12] & ~q[13]) | (q[10] & ~q[11]) | (q[8] & ~q[9]) | (q[6] & ~q[7]) | (q[4] & ~q[5]) |
+         (q[2] & ~q[3]) | (q[0] & ~q[1]);
+}
+
+RB_HD uint32_t ld32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+struct StripState {
+  uint32_t T[4][15];  // threshold planes of the last four rows (ring)
+  uint32_t O[4][4];   // ordered planes of the last four rows (ring)
+};
+
+RB_HD void load_row(const uint8_t* rowptr, uint32_t w[8]) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(rowptr);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = ld32(p + k);
+}
+
+RB_HD void row_to_planes(const uint32_t w[8], uint32_t O[4], uint32_t T[15]) {
+  uint32_t n[4];
+  bytes_to_planes(w, n);
+  O[0] = n2o_plane<0>(n); O[1] = n2o_plane<1>(n); O[2] = n2o_plane<2>(n); O[3] = n2o_plane<3>(n);
+  thresholds(O, T);
+}
+
+// One output row.  PH = ring slot of the oldest row (y-2); the new row (y+2) replaces it.
+template <int PH>
+RB_HD void strip_step(const RbKpeParams& p, StripState& st, const uint32_t wnew[8], uint32_t vmask,
+                      uint32_t* kp_out, uint32_t* w2_out, uint8_t* med_out) {
+  uint32_t On[4], Tn[15];
+  row_to_planes(wnew, On, Tn);
+  uint32_t q3[15], q5[15];
+#pragma unroll
+  for (int t = 0; t < 15; ++t)
+    rank_planes(st.T[PH][t], st.T[(PH + 1) & 3][t], st.T[(PH + 2) & 3][t], st.T[(PH + 3) & 3][t], Tn[t], q3[t], q5[t]);
+  uint32_t p3[4], p5[4];
+  thermo_to_binary(q3, p3);
+  thermo_to_binary(q5, p5);
+  const uint32_t* p1 = st.O[(PH + 2) & 3];  // centre row
+  const uint32_t ne13 = (p1[0] ^ p3[0]) | (p1[1] ^ p3[1]) | (p1[2] ^ p3[2]) | (p1[3] ^ p3[3]);
+  const uint32_t ne35 = (p3[0] ^ p5[0]) | (p3[1] ^ p5[1]) | (p3[2] ^ p5[2]) | (p3[3] ^ p5[3]);
+  const uint32_t ne15 = (p1[0] ^ p5[0]) | (p1[1] ^ p5[1]) | (p1[2] ^ p5[2]) | (p1[3] ^ p5[3]);
+  const uint32_t kp = ne13 & ne35 & vmask;  // src/kpe.hpp:316-318
+  *kp_out = kp;
+  *w2_out = kp & ne15;                      // src/kpe.hpp:319
+  if (med_out) {
+    uint32_t m[4], w[8];
+    m[0] = o2n_plane<0>(p3) & vmask; m[1] = o2n_plane<1>(p3) & vmask;
+    m[2] = o2n_plane<2>(p3) & vmask; m[3] = o2n_plane<3>(p3) & vmask;
+    planes_to_bytes(m, w);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(med_out);  // pixel 28j+2 -> byte 28j+4 of the row
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dst[k] = rb_prmt(w[k], w[k + 1], 0x5432);
+  }
+#pragma unroll
+  for (int t = 0; t < 15; ++t) st.T[PH][t] = Tn[t];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) st.O[PH][k] = On[k];
+}
+
+// The whole segment of one strip.  f = frame, s = segment, j = strip.
+RB_HD void kpe_strip(const RbKpeParams& p, uint32_t f, uint32_t s, uint32_t j) {
+  const RbGeom& g = p.g;
+  const uint32_t x0 = RB_STRIP_OUT * j;
+  uint32_t vmask = 0x3FFFFFFCu;  // bits 2..29 = output columns of this strip
+  {
+    const int maxi = (int)g.W - 3 - (int)x0;  // x <= W-3 (src/kpe.hpp:183-184)
+    if (maxi < 2) return;
+    if (maxi < 29) vmask &= (2u << maxi) - 1u;
+  }
+  const uint32_t ya = 2 + s * p.seg_rows;                                   // first output row
+  const uint32_t yend = g.H - 4;                                            // rows end at H-5 (src/kpe.hpp:268)
+  const uint32_t yb = ya + p.seg_rows < yend ? ya + p.seg_rows : yend;      // one past last output row
+  if (ya >= yb) return;
+  const uint8_t* fbase = p.frames + (uint64_t)f * g.frame_stride + x0;
+  uint32_t* kprow = p.kpbits + ((uint64_t)f * g.H + ya) * g.NS + j;
+  uint32_t* w2row = p.w2bits + ((uint64_t)f * g.H + ya) * g.NS + j;
+  uint8_t* medrow = p.median ? p.median + (uint64_t)f * g.median_stride + (uint64_t)ya * g.mpitch + x0 + 4 : nullptr;
+
+  StripState st;
+  uint32_t w[8];
+  // warm-up: rows ya-2 .. ya+1 fill ring slots 0..3
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    load_row(fbase + (uint64_t)(ya - 2 + k) * g.pitch, w);
+    row_to_planes(w, st.O[k], st.T[k]);
+  }
+  uint32_t r = ya + 2;  // input row entering; output row y = r - 2
+  load_row(fbase + (uint64_t)r * g.pitch, w);
+  const uint32_t rlast = yb + 1;  // last input row
+  while (true) {
+    uint32_t wn[8];
+#define RB_STEP(PH)                                                                         \
+    {                                                                                       \
+      const uint32_t rn = r + 1 <= rlast ? r + 1 : rlast; /* prefetch next row (clamped) */ \
+      load_row(fbase + (uint64_t)rn * g.pitch, wn);                                         \
+      strip_step<PH>(p, st, w, vmask, kprow, w2row, medrow);                                \
+      kprow += g.NS; w2row += g.NS; if (medrow) medrow += g.mpitch;                         \
+      if (r == rlast) break;                                                                \
+      ++r;                                                                                  \
+      _Pragma("unroll") for (int k = 0; k < 8; ++k) w[k] = wn[k];                           \
+    }
+    RB_STEP(0) RB_STEP(1) RB_STEP(2) RB_STEP(3)
+#undef RB_STEP
+  }
+}
+
+}  // namespace rbk
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(128) rb_kpe_kernel(const RbKpeParams p) {
+  const uint32_t items = p.nframes * p.nseg * p.g.NS;
+  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const uint32_t j = it % p.g.NS;
+    const uint32_t fs = it / p.g.NS;
+    rbk::kpe_strip(p, fs / p.nseg, fs % p.nseg, j);
+  }
+}
+#endif

@@ -103,13 +103,15 @@ def render(world: np.ndarray, path: np.ndarray, w: int, h: int) -> np.ndarray:
 def scrolling_tilemap(n: int, w: int = 320, h: int = 224, seed: int = 1, *, world_w: int = 4096,
                       world_h: int = 2048, n_tiles: int = 64, speckle: float = 0.05,
                       vmax=(4, 3), sprites: int = 0, cut_every: int = 0, levels: int = 1,
-                      parallax: int = 0, detail: int = 1) -> Sequence:
+                      parallax: int = 0, detail: int = 1, frame_range=None) -> Sequence:
     """The workload family of BASELINE.json ``configs``.
 
     sprites    number of moving textured rectangles drawn over the background (config 3)
     cut_every  mean number of frames between hard scene cuts (config 5); 0 = none
     levels     number of distinct worlds (tile sets) the cuts rotate through
     parallax   band height in pixels of a second layer scrolling at half speed; 0 = none
+    frame_range (a, b): render only frames [a, b) of the n-frame sequence (a rank's shard); path and
+               level still describe the rendered frames only
     """
     rng = np.random.default_rng(seed)
     world_w = max(world_w, w + 64)
@@ -129,6 +131,10 @@ def scrolling_tilemap(n: int, w: int = 320, h: int = 224, seed: int = 1, *, worl
             np.clip(path[i:, 1], 0, world_h - h, out=path[i:, 1])
             level[i:] = cur
             i += int(rng.integers(cut_every // 2 + 1, cut_every * 3 // 2 + 2))
+    if frame_range is not None:
+        assert sprites == 0, "sprites are stateful; render the whole sequence"
+        a, b = frame_range
+        path, level, n = path[a:b].copy(), level[a:b].copy(), b - a
     frames = np.empty((n, h, w), np.uint8)
     for i in range(n):
         x, y = int(path[i, 0]), int(path[i, 1])

@@ -1,0 +1,106 @@
+// tests/emul/emul.cpp -- HOST build of the kernel bodies for CPU unit tests.
+//
+// TEST INFRASTRUCTURE ONLY.  The CUDA kernels in remap_b200/csrc/*.cuh are written as plain
+// host+device code; this file compiles the very same source with g++ and runs every work item (or
+// every thread of a block, phase by phase) in a serial loop, so kernel logic can be diffed against
+// the oracle in the GPU-less build container.  It is never linked into libremap_b200.so and no
+// product path can reach it (the product library has no host compute path at all).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#define RB_EMUL 1
+#include "../../remap_b200/csrc/rb_host.hpp"
+#include "../../remap_b200/csrc/rb_kpe.cuh"
+
+extern "C" {
+
+// frames: n*H*W bytes (dense).  median: n*H*W (dense, may be NULL).  kp/w2: n*H*NS words.
+int emul_kpe(const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, uint32_t nseg, uint8_t* median,
+             uint32_t* kpbits, uint32_t* w2bits) {
+  RbKpeParams p;
+  if (rb_make_geom(W, H, 4, 2, 16, 10, 3, &p.g) != 0) return -1;
+  const RbGeom& g = p.g;
+  std::vector<uint8_t> dfr((size_t)g.frame_stride * n + 64, 0xEE);  // garbage beyond the rows
+  for (uint32_t f = 0; f < n; ++f)
+    for (uint32_t y = 0; y < H; ++y) memcpy(&dfr[f * g.frame_stride + (size_t)y * g.pitch], frames + ((size_t)f * H + y) * W, W);
+  std::vector<uint8_t> dmed((size_t)g.median_stride * n + 64, 0);
+  p.frames = dfr.data();
+  p.median = median ? dmed.data() : nullptr;
+  p.kpbits = kpbits;
+  p.w2bits = w2bits;
+  p.nframes = n;
+  p.nseg = nseg;
+  const uint32_t rows = H - 6;
+  p.seg_rows = (rows + nseg - 1) / nseg;
+  memset(kpbits, 0, (size_t)n * H * g.NS * 4);
+  memset(w2bits, 0, (size_t)n * H * g.NS * 4);
+  for (uint32_t f = 0; f < n; ++f)
+    for (uint32_t s = 0; s < nseg; ++s)
+      for (uint32_t j = 0; j < g.NS; ++j) rbk::kpe_strip(p, f, s, j);
+  if (median)
+    for (uint32_t f = 0; f < n; ++f)
+      for (uint32_t y = 0; y < H; ++y)
+        memcpy(median + ((size_t)f * H + y) * W, &dmed[f * g.median_stride + (size_t)y * g.mpitch + 2], W);
+  return (int)g.NS;
+}
+
+uint32_t emul_strips(uint32_t W) { return (W - 4 + RB_STRIP_OUT - 1) / RB_STRIP_OUT; }
+
+}  // extern "C"
+
+#include "../../remap_b200/csrc/rb_kpm.cuh"
+
+extern "C" {
+
+size_t emul_sizeof_vote() { return sizeof(RbRegionVote); }
+size_t emul_sizeof_result() { return sizeof(RbPairResult); }
+
+// Runs K1 (host build) on all frames, then K2 on every (pair, region) and K3 on every pair.
+// votes: (n-1)*8 RbRegionVote, results: (n-1) RbPairResult.  tap: bins of (tap_pair, tap_region).
+int emul_register(const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, uint32_t code_slots, uint32_t off_slots,
+                  uint32_t NT, RbRegionVote* votes, RbPairResult* results, int32_t tap_pair, int32_t tap_region,
+                  RbBin* tap_bins, uint32_t tap_cap, uint32_t* tap_count) {
+  RbKpmParams p;
+  memset(&p, 0, sizeof(p));
+  if (rb_make_geom(W, H, 4, 2, 16, 10, 3, &p.g) != 0) return -1;
+  const RbGeom& g = p.g;
+  std::vector<uint8_t> dfr((size_t)g.frame_stride * n + 64, 0xEE);
+  for (uint32_t f = 0; f < n; ++f)
+    for (uint32_t y = 0; y < H; ++y) memcpy(&dfr[f * g.frame_stride + (size_t)y * g.pitch], frames + ((size_t)f * H + y) * W, W);
+  std::vector<uint32_t> kp((size_t)n * H * g.NS, 0), w2((size_t)n * H * g.NS, 0);
+  {
+    RbKpeParams k;
+    k.g = g; k.frames = dfr.data(); k.median = nullptr; k.kpbits = kp.data(); k.w2bits = w2.data();
+    k.nframes = n; k.nseg = 2; k.seg_rows = (H - 6 + 1) / 2;
+    for (uint32_t f = 0; f < n; ++f)
+      for (uint32_t s = 0; s < k.nseg; ++s)
+        for (uint32_t j = 0; j < g.NS; ++j) rbk::kpe_strip(k, f, s, j);
+  }
+  uint32_t maxw = 0, maxh = 0;
+  for (uint32_t s = 0; s < g.grid_w; ++s) {
+    const uint32_t tx0 = (g.col0[s] - 2) & ~7u;
+    const uint32_t tw = (g.col1[s] + 2 - tx0 + 7) / 8;
+    if (tw > maxw) maxw = tw;
+  }
+  for (uint32_t s = 0; s < g.grid_h; ++s)
+    if (g.row1[s] - g.row0[s] > maxh) maxh = g.row1[s] - g.row0[s];
+  p.frames = dfr.data(); p.kpbits = kp.data(); p.w2bits = w2.data(); p.votes = votes;
+  p.first_frame = 0; p.npairs = n - 1; p.code_slots = code_slots; p.off_slots = off_slots;
+  p.tile_pitch = maxw + 1; p.tile_rows = maxh + 4;
+  p.tap_bins = tap_pair >= 0 ? tap_bins : nullptr; p.tap_cap = tap_cap; p.tap_count = tap_count;
+  p.tap_pair = (uint32_t)tap_pair; p.tap_region = (uint32_t)tap_region;
+  std::vector<uint32_t> smem(rbm::smem_words(p, NT) + 4);
+  for (uint32_t pair = 0; pair + 1 < n; ++pair) {
+    for (uint32_t r = 0; r < g.nreg; ++r) {
+      std::fill(smem.begin(), smem.end(), 0xDEADBEEFu);  // shared memory is not zero-initialised
+      rbm::kpm_block(p, pair, r, smem.data(), NT);
+    }
+    rbm::declare_pair(g, votes + (size_t)pair * g.nreg, results + pair);
+  }
+  return 0;
+}
+
+}  // extern "C"

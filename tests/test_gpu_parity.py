@@ -1,0 +1,185 @@
+"""-m gpu: the CUDA path (through the C ABI) against (a) committed dumps of the REAL reference,
+(b) the C restatement on seeded inputs, (c) size-independent properties at BASELINE sizes."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import gpu_common
+import parity
+import remap_b200
+from oracle import oracle, refdump
+from remap_b200 import RB_OFFSET_TIE_SENSITIVE, RB_OFFSET_VALID, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not p.endswith("fgmask.npz"))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_cuda_matches_reference_dump(name, golden_dir):
+    """Every intermediate the reference produced for this fixture, byte for byte."""
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    frames = z["frames"]
+    ref = refdump.parse_dump(z["dump"].tobytes())
+    n = frames.shape[0]
+    out = gpu_common.run_sequence(frames)
+    reg = out["reg"]
+    try:
+        valid, dx, dy, flagged = [], [], [], 0
+        for i in range(n):
+            parity.check_frame(ref["frames"][i], out["medians"][i], reg.keypoints(i), f"{name} frame {i}")
+            if i > 0:
+                ballots = reg.region_ballots(i - 1)
+                bins = [reg.region_votes(i - 1, r) for r in range(8)]
+                rec = gpu_common.result_record(out["offsets"][i - 1], ballots)
+                st = parity.check_pair(ref["pairs"][i - 1], rec, ballots, bins, f"{name} pair {i}")
+                flagged += st == "flagged"
+                valid.append(rec["valid"]); dx.append(rec["dx"]); dy.append(rec["dy"])
+        if flagged == 0:  # positions of the unmodified frc::collector loop
+            assert np.array_equal(parity.positions_from_results(valid, dx, dy), ref["positions"])
+        if name != "parallax":
+            assert flagged == 0
+    finally:
+        reg.close()
+
+
+ORACLE_CASES = {
+    "S": (lambda: synth.scrolling_tilemap(6, 320, 224, seed=31).frames, {}),
+    "S_dense": (lambda: synth.scrolling_tilemap(4, 320, 224, seed=32, speckle=0.10, detail=3).frames, {}),
+    "S_repeat": (lambda: synth.scrolling_tilemap(4, 320, 224, seed=33, speckle=0.10, n_tiles=4).frames, {}),
+    "S_small_tables": (lambda: synth.scrolling_tilemap(4, 320, 224, seed=34, speckle=0.10, n_tiles=4).frames,
+                       dict(code_slots=256, offset_slots=1024)),
+    "L": (lambda: synth.scrolling_tilemap(3, 640, 480, seed=35, speckle=0.10, vmax=(48, 48)).frames, {}),
+    "odd": (lambda: synth.scrolling_tilemap(4, 323, 227, seed=36).frames, {}),
+    "random16": (lambda: synth.random_frames(3, 320, 224, seed=37), {}),
+    "random2": (lambda: synth.random_frames(3, 160, 112, seed=38, palette=2), {}),
+    "cuts": (lambda: synth.scrolling_tilemap(8, 320, 224, seed=39, cut_every=3, levels=2).frames, {}),
+    "sprites": (lambda: synth.scrolling_tilemap(5, 320, 224, seed=40, sprites=12).frames, {}),
+    "zeros": (lambda: np.zeros((3, 224, 320), np.uint8), {}),
+    "two_frames": (lambda: synth.scrolling_tilemap(2, 320, 224, seed=41).frames, {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ORACLE_CASES))
+def test_cuda_matches_oracle(name):
+    make, kw = ORACLE_CASES[name]
+    frames = make()
+    gpu_common.compare_with_oracle(frames, oracle, name, taps=((0, 0), (0, 3), (0, 7), (frames.shape[0] - 2, 5)), **kw)
+
+
+def test_dirty_high_nibbles_are_ignored():
+    """The reference requires 0..15 (src/cpl.hpp LUT index); the kernels mask to the low nibble."""
+    frames = synth.scrolling_tilemap(3, 320, 224, seed=42).frames
+    a = gpu_common.run_sequence(frames)
+    b = gpu_common.run_sequence(frames | 0xA0)
+    try:
+        assert np.array_equal(a["offsets"], b["offsets"]) and np.array_equal(a["medians"], b["medians"])
+    finally:
+        a["reg"].close(); b["reg"].close()
+
+
+def test_full_size_config2_properties():
+    """BASELINE config 2: 320x224, 20,000 frames on one GPU.  Size-independent checks:
+    ground-truth camera deltas, range-split invariance (== the multi-GPU sharding rule), determinism,
+    and a sampled diff against the oracle."""
+    n = 20000
+    seq = synth.scrolling_tilemap(n, 320, 224, seed=1)
+    with remap_b200.Registrar(320, 224, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off, _ = reg.register(n)
+        assert (off["flags"] & RB_OFFSET_VALID).all()
+        assert not (off["flags"] & RB_OFFSET_TIE_SENSITIVE).any()
+        assert np.array_equal(np.stack([off["dx"], off["dy"]], 1), seq.true_offsets)
+        # determinism
+        off2, _ = reg.register(n)
+        assert np.array_equal(off, off2)
+        # contiguous ranges with a one-frame overlap give the same pairs
+        cut = 7777
+        a, _ = reg.register(cut + 1, first=0)
+        a = a.copy()
+        b, _ = reg.register(n - cut, first=cut)
+        assert np.array_equal(np.concatenate([a, b]), off)
+        # sampled medians / keypoints against the oracle
+        cfg = oracle.config(320, 224)
+        rng = np.random.default_rng(0)
+        reg.register(n)
+        for i in rng.integers(0, n, size=12):
+            omed, okps = oracle.extract(cfg, seq.frames[i])
+            assert np.array_equal(reg.fetch_medians(1, first=int(i))[0], omed)
+            kps = reg.keypoints(int(i))
+            assert np.array_equal(kps["x"], okps["x"]) and np.array_equal(kps["code"], okps["code"])
+
+
+def test_full_size_640x480_properties():
+    """BASELINE config 4: 640x480, large scroll offsets, dense keypoints."""
+    n = 600
+    seq = synth.scrolling_tilemap(n, 640, 480, seed=4, speckle=0.10, vmax=(48, 48))
+    with remap_b200.Registrar(640, 480, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off, _ = reg.register(n)
+        ok = (off["flags"] & RB_OFFSET_VALID) != 0
+        assert ok.all()
+        assert np.array_equal(np.stack([off["dx"], off["dy"]], 1), seq.true_offsets)
+
+
+def test_scene_cuts_start_new_fragments():
+    """Config 5 flavour: hard cuts between levels must give 'no offset' exactly at the cuts."""
+    n = 400
+    seq = synth.scrolling_tilemap(n, 320, 224, seed=5, cut_every=40, levels=3)
+    cuts = np.nonzero(seq.level[1:] != seq.level[:-1])[0]
+    assert len(cuts) > 3
+    with remap_b200.Registrar(320, 224, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off, _ = reg.register(n)
+    valid = (off["flags"] & RB_OFFSET_VALID) != 0
+    assert not valid[cuts].any()
+    keep = np.ones(n - 1, bool); keep[cuts] = False
+    assert valid[keep].all()
+    assert np.array_equal(np.stack([off["dx"], off["dy"]], 1)[keep], seq.true_offsets[keep])
+
+
+def test_foreground_mask_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "fgmask.npz"))
+    bg = z["bg"]
+    for k in range(int(z["n"])):
+        px, py = (int(v) for v in z[f"pos{k}"])
+        frame = z[f"frame{k}"]
+        H, W = frame.shape
+        if W / 4 <= 8 or H / 2 <= 8:
+            continue  # smaller than any registrable window
+        with remap_b200.Registrar(W, H, max_frames=2) as reg:
+            assert np.array_equal(reg.foreground_mask(bg, px, py, frame), z[f"mask{k}"])
+
+
+def test_foreground_mask_sprites_vs_oracle():
+    """Config 3 flavour: sprites over a scrolling background; mask against the true background."""
+    seq = synth.scrolling_tilemap(6, 320, 224, seed=6, sprites=10)
+    clean = synth.scrolling_tilemap(6, 320, 224, seed=6, sprites=0)
+    H, W = 224, 320
+    x0, y0 = seq.path[:, 0].min(), seq.path[:, 1].min()
+    x1, y1 = seq.path[:, 0].max() + W, seq.path[:, 1].max() + H
+    bg = np.zeros((y1 - y0, x1 - x0), np.uint8)
+    for i in range(6):
+        px, py = seq.path[i] - (x0, y0)
+        bg[py:py + H, px:px + W] = clean.frames[i]
+    with remap_b200.Registrar(W, H, max_frames=8) as reg:
+        reg.upload(seq.frames)
+        for i in range(6):
+            px, py = (int(v) for v in seq.path[i] - (x0, y0))
+            want = oracle.foreground_mask(bg, px, py, seq.frames[i])
+            assert np.array_equal(reg.foreground_mask(bg, px, py, seq.frames[i]), want)
+            assert np.array_equal(reg.foreground_mask_resident(bg, px, py, i), want)
+            assert (want == 0).any() and (want == 255).any()
+
+
+def test_errors_are_reported_not_thrown():
+    with remap_b200.Registrar(320, 224, max_frames=4) as reg:
+        with pytest.raises(remap_b200.RemapError):
+            reg.register(3)  # nothing uploaded
+        with pytest.raises(remap_b200.RemapError):
+            reg.upload(np.zeros((5, 224, 320), np.uint8))  # beyond capacity
+    with pytest.raises(remap_b200.RemapError):
+        remap_b200.Registrar(16, 16, max_frames=4)  # too small for the 4x2 grid
