@@ -341,30 +341,51 @@ void ro_declare(const ro_config* cfg, const ro_region_vote* votes, ro_match_resu
   if (b1 >= 0 && S0 < S1 + half) res->valid = 0;
   else { res->valid = 1; res->dx = cand[b0].dx; res->dy = cand[b0].dy; }
 
-  /* tie sensitivity: how far can any permutation of count-tied bins move the Borda scores? */
-  uint32_t G = 0, Lmax = 0, Lw = 0;
-  for (uint32_t r = 0; r < nreg; ++r) {
-    const ro_region_vote* v = &votes[r];
-    uint32_t gain = 0, lossmax = 0;
-    for (uint32_t k = 0; k < v->nticket; ++k) {
-      uint32_t pts = rv - k;
-      uint32_t maxpts = v->ngt[k] < rv ? rv - v->ngt[k] : 0;          /* best position = ngt      */
-      uint32_t worst = v->nge[k] - 1;                                  /* worst position = nge - 1 */
-      uint32_t minpts = worst < rv ? rv - worst : 0;
-      if (maxpts - pts > gain) gain = maxpts - pts;
-      if (pts - minpts > lossmax) lossmax = pts - minpts;
-      if (v->ticket[k].dx == cand[b0].dx && v->ticket[k].dy == cand[b0].dy) Lw += pts - minpts;
+  /* Tie sensitivity.  Under ANY order of count-tied bins, an offset o scores between
+   *   lo(o) = sum_r minpts_r(o)   and   hi(o) = sum_r maxpts_r(o)
+   * where, in region r: o on the ticket at k -> best position ngt[k], worst position nge[k]-1;
+   * o off the ticket -> it can only enter if the ticket is full and its last entry's count is shared
+   * with bins outside the ticket (nge[rv-1] > rv), and then at best at position ngt[rv-1].
+   * An offset on no ticket at all scores at most hi_out.  Declared w is tie-proof iff
+   * lo(w) >= max_{o != w} hi(o) + max(half, 1); "none" is tie-proof iff the two largest lo() keep two
+   * candidates alive (second >= 1) and max hi() < second lo + half. */
+  {
+    uint32_t lo[RO_MAX_REGIONS * 3], hi[RO_MAX_REGIONS * 3], hi_out = 0;
+    int ambiguous = 0;
+    for (uint32_t j = 0; j < ncand; ++j) lo[j] = hi[j] = 0;
+    for (uint32_t r = 0; r < nreg; ++r) {
+      const ro_region_vote* v = &votes[r];
+      uint32_t og = 0;
+      if (v->nticket == rv && v->nge[rv - 1] > rv) og = v->ngt[rv - 1] < rv ? rv - v->ngt[rv - 1] : 0;
+      hi_out += og;
+      for (uint32_t j = 0; j < ncand; ++j) {
+        uint32_t k;
+        for (k = 0; k < v->nticket; ++k)
+          if (v->ticket[k].dx == cand[j].dx && v->ticket[k].dy == cand[j].dy) break;
+        if (k < v->nticket) {
+          uint32_t worst = v->nge[k] - 1;
+          hi[j] += v->ngt[k] < rv ? rv - v->ngt[k] : 0;
+          lo[j] += worst < rv ? rv - worst : 0;
+          if (v->nge[k] != v->ngt[k] + 1) ambiguous = 1; /* shares its count with another bin */
+        } else {
+          hi[j] += og;
+        }
+      }
     }
-    if (v->nticket == rv && v->nticket > 0 && v->nge[rv - 1] > rv) { /* bins outside the ticket tied with its last entry */
-      uint32_t og = v->ngt[rv - 1] < rv ? rv - v->ngt[rv - 1] : 0;
-      if (og > gain) gain = og;
+    if (!ambiguous) res->tie_sensitive = 0;
+    else if (res->valid) {
+      uint32_t H = hi_out;
+      for (uint32_t j = 0; j < ncand; ++j) if ((int)j != b0 && hi[j] > H) H = hi[j];
+      res->tie_sensitive = !(lo[b0] >= H + (half > 1 ? half : 1));
+    } else {
+      uint32_t H = hi_out, l1 = 0, l2 = 0;
+      for (uint32_t j = 0; j < ncand; ++j) {
+        if (hi[j] > H) H = hi[j];
+        if (lo[j] > l1) { l2 = l1; l1 = lo[j]; } else if (lo[j] > l2) l2 = lo[j];
+      }
+      res->tie_sensitive = !(l2 >= 1 && H < l2 + half);
     }
-    G += gain;
-    Lmax += lossmax;
   }
-  if (G == 0 && Lmax == 0) res->tie_sensitive = 0;
-  else if (res->valid) res->tie_sensitive = !((int64_t)S0 - Lw >= (int64_t)S1 + G + half);
-  else res->tie_sensitive = !((int64_t)S1 - Lmax >= 1 && (int64_t)S0 + G < (int64_t)S1 - Lmax + half);
 }
 
 /* kpm::match for one consecutive pair.  region_votes_out: nreg entries (may be NULL). */

@@ -456,29 +456,43 @@ RB_HD void declare_pair(const RbGeom& g, const RbRegionVote* votes, RbPairResult
       const uint32_t S0 = csc[b0], S1 = b1 >= 0 ? csc[b1] : 0;
       if (b1 >= 0 && S0 < S1 + half) r.valid = 0;
       else { r.valid = 1; r.dx = cdx[b0]; r.dy = cdy[b0]; }
-      uint32_t G = 0, Lmax = 0, Lw = 0;
+      // Tie sensitivity: bounds lo(o) <= score(o) <= hi(o) under any order of count-tied bins; see
+      // ro_declare in the oracle and DESIGN.md for the derivation.
+      uint32_t lo[RB_MAX_REGIONS * 3], hi[RB_MAX_REGIONS * 3], hi_out = 0;
+      bool ambiguous = false;
+      for (uint32_t j = 0; j < nc; ++j) lo[j] = hi[j] = 0;
       for (uint32_t i = 0; i < nreg; ++i) {
         const RbRegionVote& v = votes[i];
-        uint32_t gain = 0, lossmax = 0;
-        for (uint32_t k = 0; k < v.nticket; ++k) {
-          const uint32_t pts = rv - k;
-          const uint32_t maxpts = v.ngt[k] < rv ? rv - v.ngt[k] : 0;
-          const uint32_t worst = v.nge[k] - 1;
-          const uint32_t minpts = worst < rv ? rv - worst : 0;
-          if (maxpts - pts > gain) gain = maxpts - pts;
-          if (pts - minpts > lossmax) lossmax = pts - minpts;
-          if (v.ticket[k].dx == cdx[b0] && v.ticket[k].dy == cdy[b0]) Lw += pts - minpts;
+        uint32_t og = 0;
+        if (v.nticket == rv && v.nge[rv - 1] > rv) og = v.ngt[rv - 1] < rv ? rv - v.ngt[rv - 1] : 0;
+        hi_out += og;
+        for (uint32_t j = 0; j < nc; ++j) {
+          uint32_t k = 0;
+          while (k < v.nticket && !(v.ticket[k].dx == cdx[j] && v.ticket[k].dy == cdy[j])) ++k;
+          if (k < v.nticket) {
+            const uint32_t worst = v.nge[k] - 1;
+            hi[j] += v.ngt[k] < rv ? rv - v.ngt[k] : 0;
+            lo[j] += worst < rv ? rv - worst : 0;
+            if (v.nge[k] != v.ngt[k] + 1) ambiguous = true;
+          } else {
+            hi[j] += og;
+          }
         }
-        if (v.nticket == rv && v.nge[rv - 1] > rv) {
-          const uint32_t og = v.ngt[rv - 1] < rv ? rv - v.ngt[rv - 1] : 0;
-          if (og > gain) gain = og;
-        }
-        G += gain;
-        Lmax += lossmax;
       }
-      if (G == 0 && Lmax == 0) r.tie_sensitive = 0;
-      else if (r.valid) r.tie_sensitive = !((long long)S0 - Lw >= (long long)S1 + G + half);
-      else r.tie_sensitive = !((long long)S1 - Lmax >= 1 && (long long)S0 + G < (long long)S1 - Lmax + half);
+      if (!ambiguous) r.tie_sensitive = 0;
+      else if (r.valid) {
+        uint32_t Hm = hi_out;
+        for (uint32_t j = 0; j < nc; ++j)
+          if ((int)j != b0 && hi[j] > Hm) Hm = hi[j];
+        r.tie_sensitive = !(lo[b0] >= Hm + (half > 1 ? half : 1));
+      } else {
+        uint32_t Hm = hi_out, l1 = 0, l2 = 0;
+        for (uint32_t j = 0; j < nc; ++j) {
+          if (hi[j] > Hm) Hm = hi[j];
+          if (lo[j] > l1) { l2 = l1; l1 = lo[j]; } else if (lo[j] > l2) l2 = lo[j];
+        }
+        r.tie_sensitive = !(l2 >= 1 && Hm < l2 + half);
+      }
     }
   }
   *res = r;
