@@ -254,10 +254,10 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   const uint32_t area = maxcols * maxh;
   c->code_slots = cfg->code_slots ? cfg->code_slots : next_pow2(area / 4 < 1024 ? 1024 : area / 4);
   c->off_slots = cfg->offset_slots ? cfg->offset_slots : 1024;
-  if (c->code_slots > 16384 && !cfg->code_slots) c->code_slots = 16384;
+  if (c->code_slots > 8192 && !cfg->code_slots) c->code_slots = 8192;  // 12-bit list index in the code table
   if ((c->code_slots & (c->code_slots - 1)) || (c->off_slots & (c->off_slots - 1)) || c->code_slots < 64 ||
-      c->code_slots / 2 < maxcols || c->off_slots <= 2 * 256) {
-    c->err = "code_slots / offset_slots must be powers of two, code_slots/2 >= region width, offset_slots > 512";
+      c->code_slots > 8192 || c->code_slots / 2 < maxcols || c->off_slots <= 2 * 256) {
+    c->err = "code_slots / offset_slots must be powers of two, 64 <= code_slots <= 8192, code_slots/2 >= region width, offset_slots > 512";
     return RB_ERR_INVALID;
   }
   int smem_max = 0;

@@ -167,8 +167,8 @@ RB_HD uint32_t ld32(const uint32_t* p) {
 }
 
 struct StripState {
-  uint32_t T[4][15];  // threshold planes of the last four rows (ring)
-  uint32_t O[4][4];   // ordered planes of the last four rows (ring)
+  uint32_t T[4][15];  // threshold planes of rows y-2 .. y+1 (slot 0 = oldest)
+  uint32_t O[4][4];   // ordered planes of the same rows
 };
 
 RB_HD void load_row(const uint8_t* rowptr, uint32_t w[8]) {
@@ -184,20 +184,21 @@ RB_HD void row_to_planes(const uint32_t w[8], uint32_t O[4], uint32_t T[15]) {
   thresholds(O, T);
 }
 
-// One output row.  PH = ring slot of the oldest row (y-2); the new row (y+2) replaces it.
-template <int PH>
-RB_HD void strip_step(const RbKpeParams& p, StripState& st, const uint32_t wnew[8], uint32_t vmask,
-                      uint32_t* kp_out, uint32_t* w2_out, uint8_t* med_out) {
+// One output row y: st holds rows y-2 .. y+1, wnew is row y+2.  Afterwards st holds y-1 .. y+2.
+// The body is deliberately NOT unrolled over rows: one step is ~1000 SASS instructions (16 KB) and
+// must stay resident in the instruction cache (an earlier 4x-unrolled version was instruction-fetch
+// bound, profiles/README.md); the register rotation at the end is plain MOVs.
+RB_HD void strip_step(StripState& st, const uint32_t wnew[8], uint32_t vmask, uint32_t* kp_out, uint32_t* w2_out,
+                      uint8_t* med_out) {
   uint32_t On[4], Tn[15];
   row_to_planes(wnew, On, Tn);
   uint32_t q3[15], q5[15];
 #pragma unroll
-  for (int t = 0; t < 15; ++t)
-    rank_planes(st.T[PH][t], st.T[(PH + 1) & 3][t], st.T[(PH + 2) & 3][t], st.T[(PH + 3) & 3][t], Tn[t], q3[t], q5[t]);
+  for (int t = 0; t < 15; ++t) rank_planes(st.T[0][t], st.T[1][t], st.T[2][t], st.T[3][t], Tn[t], q3[t], q5[t]);
   uint32_t p3[4], p5[4];
   thermo_to_binary(q3, p3);
   thermo_to_binary(q5, p5);
-  const uint32_t* p1 = st.O[(PH + 2) & 3];  // centre row
+  const uint32_t* p1 = st.O[2];  // centre row
   const uint32_t ne13 = (p1[0] ^ p3[0]) | (p1[1] ^ p3[1]) | (p1[2] ^ p3[2]) | (p1[3] ^ p3[3]);
   const uint32_t ne35 = (p3[0] ^ p5[0]) | (p3[1] ^ p5[1]) | (p3[2] ^ p5[2]) | (p3[3] ^ p5[3]);
   const uint32_t ne15 = (p1[0] ^ p5[0]) | (p1[1] ^ p5[1]) | (p1[2] ^ p5[2]) | (p1[3] ^ p5[3]);
@@ -214,9 +215,9 @@ RB_HD void strip_step(const RbKpeParams& p, StripState& st, const uint32_t wnew[
     for (int k = 0; k < 7; ++k) dst[k] = rb_prmt(w[k], w[k + 1], 0x5432);
   }
 #pragma unroll
-  for (int t = 0; t < 15; ++t) st.T[PH][t] = Tn[t];
+  for (int t = 0; t < 15; ++t) { st.T[0][t] = st.T[1][t]; st.T[1][t] = st.T[2][t]; st.T[2][t] = st.T[3][t]; st.T[3][t] = Tn[t]; }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) st.O[PH][k] = On[k];
+  for (int k = 0; k < 4; ++k) { st.O[0][k] = st.O[1][k]; st.O[1][k] = st.O[2][k]; st.O[2][k] = st.O[3][k]; st.O[3][k] = On[k]; }
 }
 
 // The whole segment of one strip.  f = frame, s = segment, j = strip.
@@ -240,29 +241,29 @@ RB_HD void kpe_strip(const RbKpeParams& p, uint32_t f, uint32_t s, uint32_t j) {
 
   StripState st;
   uint32_t w[8];
-  // warm-up: rows ya-2 .. ya+1 fill ring slots 0..3
-#pragma unroll
+  // warm-up: rows ya-2 .. ya+1
+#pragma unroll 1
   for (int k = 0; k < 4; ++k) {
     load_row(fbase + (uint64_t)(ya - 2 + k) * g.pitch, w);
-    row_to_planes(w, st.O[k], st.T[k]);
+    uint32_t On[4], Tn[15];
+    row_to_planes(w, On, Tn);
+#pragma unroll
+    for (int t = 0; t < 15; ++t) { st.T[0][t] = st.T[1][t]; st.T[1][t] = st.T[2][t]; st.T[2][t] = st.T[3][t]; st.T[3][t] = Tn[t]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { st.O[0][q] = st.O[1][q]; st.O[1][q] = st.O[2][q]; st.O[2][q] = st.O[3][q]; st.O[3][q] = On[q]; }
   }
-  uint32_t r = ya + 2;  // input row entering; output row y = r - 2
-  load_row(fbase + (uint64_t)r * g.pitch, w);
   const uint32_t rlast = yb + 1;  // last input row
-  while (true) {
+  load_row(fbase + (uint64_t)(ya + 2) * g.pitch, w);
+#pragma unroll 1
+  for (uint32_t r = ya + 2; r <= rlast; ++r) {  // input row r enters, output row y = r - 2
     uint32_t wn[8];
-#define RB_STEP(PH)                                                                         \
-    {                                                                                       \
-      const uint32_t rn = r + 1 <= rlast ? r + 1 : rlast; /* prefetch next row (clamped) */ \
-      load_row(fbase + (uint64_t)rn * g.pitch, wn);                                         \
-      strip_step<PH>(p, st, w, vmask, kprow, w2row, medrow);                                \
-      kprow += g.NS; w2row += g.NS; if (medrow) medrow += g.mpitch;                         \
-      if (r == rlast) break;                                                                \
-      ++r;                                                                                  \
-      _Pragma("unroll") for (int k = 0; k < 8; ++k) w[k] = wn[k];                           \
-    }
-    RB_STEP(0) RB_STEP(1) RB_STEP(2) RB_STEP(3)
-#undef RB_STEP
+    const uint32_t rn = r + 1 <= rlast ? r + 1 : rlast;  // prefetch the next row (clamped)
+    load_row(fbase + (uint64_t)rn * g.pitch, wn);
+    strip_step(st, w, vmask, kprow, w2row, medrow);
+    kprow += g.NS; w2row += g.NS;
+    if (medrow) medrow += g.mpitch;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = wn[k];
   }
 }
 

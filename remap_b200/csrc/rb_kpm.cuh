@@ -48,20 +48,25 @@ namespace rbm {
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
 
 struct Smem {  // carved from dynamic shared memory, all uint32_t-aligned
-  uint32_t* tile[2];     // [tile_rows][tile_pitch]
+  uint32_t* tile[2];     // [tile_rows][tile_pitch] packed 4 bit/pixel tiles of prev / curr frame
   uint32_t* rowcnt[4];   // per region row: prev all, prev w2, curr all, curr w2
-  uint32_t* ctag;        // [code_slots]
-  uint32_t* cpos;        // [code_slots]
+  uint32_t* segend[2];   // slow path only: row ends of the prev bands / curr chunks
+  uint32_t* ctab;        // [code_slots] 19-bit hash tag (bits 12..30) | 12-bit index into plist; never == EMPTY
+  uint32_t* plist;       // [code_slots / 2] previous keypoints of the band, (y << 16) | x
+  uint32_t* clist;       // [code_slots / 2] current keypoints of the chunk
   uint32_t* okey;        // [off_slots]
   uint32_t* ocnt;        // [off_slots]
   uint32_t* touched;     // [off_slots / 2 + NT + 1] slots claimed in this partition
   uint32_t* scal;        // scalars, see S_*
   unsigned long long* best;  // [4]: per-partition selection rounds
 };
-enum { S_NPREV = 0, S_W2PREV, S_NCURR, S_W2CURR, S_NTOUCHED, S_OVERFLOW, S_NGT0, S_NGE0 = S_NGT0 + 3, S_COUNT = S_NGE0 + 3 };
+enum {
+  S_NPREV = 0, S_W2PREV, S_NCURR, S_W2CURR, S_NTOUCHED, S_OVERFLOW, S_NGT0, S_NGE0 = S_NGT0 + 3,
+  S_PFILL = S_NGE0 + 3, S_CFILL, S_NBAND, S_NCHUNK, S_COUNT
+};
 
 RB_HD size_t smem_words(const RbKpmParams& p, uint32_t NT) {
-  return (size_t)2 * p.tile_rows * p.tile_pitch + 4 * (size_t)p.tile_rows + 2 * (size_t)p.code_slots +
+  return (size_t)2 * p.tile_rows * p.tile_pitch + 6 * (size_t)p.tile_rows + 2 * (size_t)p.code_slots +
          2 * (size_t)p.off_slots + (p.off_slots / 2 + NT + 1) + S_COUNT + 2 /*align*/ + 8 /*best*/;
 }
 
@@ -70,8 +75,10 @@ RB_HD void carve(const RbKpmParams& p, uint32_t NT, uint32_t* base, Smem& s) {
   s.tile[0] = q; q += (size_t)p.tile_rows * p.tile_pitch;
   s.tile[1] = q; q += (size_t)p.tile_rows * p.tile_pitch;
   for (int k = 0; k < 4; ++k) { s.rowcnt[k] = q; q += p.tile_rows; }
-  s.ctag = q; q += p.code_slots;
-  s.cpos = q; q += p.code_slots;
+  for (int k = 0; k < 2; ++k) { s.segend[k] = q; q += p.tile_rows; }
+  s.ctab = q; q += p.code_slots;
+  s.plist = q; q += p.code_slots / 2;
+  s.clist = q; q += p.code_slots / 2;
   s.okey = q; q += p.off_slots;
   s.ocnt = q; q += p.off_slots;
   s.touched = q; q += p.off_slots / 2 + NT + 1;
@@ -144,6 +151,24 @@ RB_HD RbBin sel_decode(unsigned long long k) {
   return b;
 }
 
+// Appends the keypoints of one region row (strip words [j0, j0+nstr) masked to [X0, X1)) to a list.
+RB_HD void emit_row(const uint32_t* bits, uint64_t rowbase, uint32_t j0, uint32_t nstr, uint32_t X0, uint32_t X1,
+                    uint32_t y, uint32_t* list, uint32_t at) {
+  for (uint32_t k = 0; k < nstr; ++k) {
+    const uint32_t j = j0 + k;
+#if defined(__CUDA_ARCH__)
+    uint32_t w = __ldg(bits + rowbase + j) & colmask(X0, X1, j);
+#else
+    uint32_t w = bits[rowbase + j] & colmask(X0, X1, j);
+#endif
+    while (w) {
+      const uint32_t b = rb_ffs0(w);
+      w &= w - 1;
+      list[at++] = (y << 16) | (RB_STRIP_OUT * j + b);
+    }
+  }
+}
+
 // One (pair, region).  smem_base: dynamic shared memory (device) or a heap buffer (host test).
 RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint32_t* smem_base, uint32_t NT) {
   const RbGeom& g = p.g;
@@ -159,50 +184,63 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
   const uint32_t nstr = j1 - j0 + 1;
   const uint32_t fprev = p.first_frame + pair, fcurr = fprev + 1;
   const bool tap = p.tap_bins != nullptr && pair == p.tap_pair && region == p.tap_region;
+  const uint64_t kprow_prev = ((uint64_t)fprev * g.H + Y0) * g.NS, kprow_curr = ((uint64_t)fcurr * g.H + Y0) * g.NS;
 
-  // ---- phase 0: zero scalars/row counters, load + pack both tiles -----------------------------
+  // ---- phase Z: zero the scalars ----------------------------------------------------------------
   RB_FOR_THREADS(tid, NT) {
     for (uint32_t i = tid; i < S_COUNT; i += NT) s.scal[i] = 0;
-    for (uint32_t i = tid; i < 4 * p.tile_rows; i += NT) s.rowcnt[0][i] = 0;  // the four arrays are contiguous
+    if (tid < 4) s.best[tid] = 0;
+  }
+  RB_SYNC();
+
+  // ---- phase 0: load + pack both tiles; per-row keypoint counts (all / weight 2) ------------------
+  RB_FOR_THREADS(tid, NT) {
+    // tiles: KW = power of two >= tw + 1 columns per row so that row/column come from shifts
+    uint32_t lkw = 4;
+    while ((1u << lkw) < tw + 1) ++lkw;
+    const uint32_t KW = 1u << lkw;
+    const uint32_t items = th << lkw;
     for (uint32_t fr = 0; fr < 2; ++fr) {
       const uint8_t* base = p.frames + (uint64_t)(fr ? fcurr : fprev) * g.frame_stride + (uint64_t)(Y0 - 2) * g.pitch + tx0;
-      for (uint32_t i = tid; i < th * (tw + 1); i += NT) {
-        const uint32_t row = i / (tw + 1), k = i % (tw + 1);
-        uint32_t v = 0;
-        if (k < tw) {
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (uint64_t)row * g.pitch + 8 * k);
+      uint32_t* dst = s.tile[fr];
+      for (uint32_t i0 = tid; i0 < items; i0 += 4 * NT) {
+        uint32_t lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // issue the loads of four rows before packing any
+          const uint32_t i = i0 + u * NT, row = i >> lkw, k = i & (KW - 1);
+          lo[u] = hi[u] = 0;
+          if (i < items && k < tw) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (uint64_t)row * g.pitch + 8 * k);
 #if defined(__CUDA_ARCH__)
-          const uint2 ab = __ldg(reinterpret_cast<const uint2*>(src));
-          v = pack8(ab.x, ab.y);
+            const uint2 ab = __ldg(reinterpret_cast<const uint2*>(src));
+            lo[u] = ab.x; hi[u] = ab.y;
 #else
-          v = pack8(src[0], src[1]);
+            lo[u] = src[0]; hi[u] = src[1];
 #endif
+          }
         }
-        s.tile[fr][(size_t)row * p.tile_pitch + k] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + u * NT, row = i >> lkw, k = i & (KW - 1);
+          if (i < items && k <= tw) dst[(size_t)row * p.tile_pitch + k] = pack8(lo[u], hi[u]);  // k == tw: pad word 0
+        }
       }
     }
-  }
-  RB_SYNC();
-
-#define RB_COLMASK(j) colmask(X0, X1, (j))
-
-  // ---- phase 1: per-row keypoint counts (all / weight 2) of both frames -----------------------
-  RB_FOR_THREADS(tid, NT) {
-    for (uint32_t i = tid; i < 2 * nrows * nstr; i += NT) {
-      const uint32_t fr = i / (nrows * nstr), rem = i % (nrows * nstr);
-      const uint32_t row = rem / nstr, j = j0 + rem % nstr;
-      const uint64_t widx = ((uint64_t)(fr ? fcurr : fprev) * g.H + (Y0 + row)) * g.NS + j;
-      const uint32_t m = RB_COLMASK(j);
-      const uint32_t a = p.kpbits[widx] & m, b = p.w2bits[widx] & m;
-      if (a) rb_atomic_add(&s.rowcnt[2 * fr][row], rb_popc(a));
-      if (b) rb_atomic_add(&s.rowcnt[2 * fr + 1][row], rb_popc(b));
+    // counts: one thread per (frame, row)
+    for (uint32_t i = tid; i < 2 * nrows; i += NT) {
+      const uint32_t fr = i >= nrows ? 1u : 0u, row = fr ? i - nrows : i;
+      const uint64_t rb = (fr ? kprow_curr : kprow_prev) + (uint64_t)row * g.NS;
+      uint32_t ca = 0, cb = 0;
+      for (uint32_t k = 0; k < nstr; ++k) {
+        const uint32_t m = colmask(X0, X1, j0 + k);
+        ca += rb_popc(p.kpbits[rb + j0 + k] & m);
+        cb += rb_popc(p.w2bits[rb + j0 + k] & m);
+      }
+      s.rowcnt[2 * fr][row] = ca;
+      s.rowcnt[2 * fr + 1][row] = cb;
+      if (ca) rb_atomic_add(&s.scal[S_NPREV + 2 * fr], ca);
+      if (cb) rb_atomic_add(&s.scal[S_W2PREV + 2 * fr], cb);
     }
-  }
-  RB_SYNC();
-  RB_FOR_THREADS(tid, NT) {
-    for (uint32_t row = tid; row < nrows; row += NT)
-      for (int k = 0; k < 4; ++k)
-        if (s.rowcnt[k][row]) rb_atomic_add(&s.scal[S_NPREV + k], s.rowcnt[k][row]);
   }
   RB_SYNC();
 
@@ -210,117 +248,159 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
   const uint32_t n_curr = s.scal[S_NCURR], w2_curr = s.scal[S_W2CURR];
   // src/kpm.hpp:219-220 ('<' on previous, '<=' on current)
   const bool use_all = (w2_prev < g.weight_switch) || (w2_curr <= g.weight_switch);
-  const uint32_t* prow = use_all ? s.rowcnt[0] : s.rowcnt[1];  // effective previous keypoints per row
+  const uint32_t* prow = use_all ? s.rowcnt[0] : s.rowcnt[1];  // effective keypoints per row
+  const uint32_t* crow = use_all ? s.rowcnt[2] : s.rowcnt[3];
   const uint32_t eff_prev = use_all ? n_prev : w2_prev;
   const uint32_t eff_curr = use_all ? n_curr : w2_curr;
   const uint32_t* kp_src = use_all ? p.kpbits : p.w2bits;      // !use_all: weight-2 codes only (src/kpm.hpp:113-117)
 
   const uint32_t rv = g.region_votes;
-  const uint32_t code_cap = p.code_slots / 2, off_cap = p.off_slots / 2;
+  const uint32_t lcap = p.code_slots / 2, off_cap = p.off_slots / 2;
   unsigned long long gtop[3] = {0, 0, 0};
   uint32_t nbins = 0;
   uint32_t Q = 1;
 
   if (eff_prev != 0 && eff_curr != 0) {
+    // Row bands of the previous frame / row chunks of the current frame that fit the lists.  The
+    // common case is one band and one chunk; otherwise two threads cut the rows serially.
+    const bool fast = eff_prev <= lcap && eff_curr <= lcap;
+    if (!fast) {
+      RB_FOR_THREADS(tid, NT) {
+        if (tid < 2) {
+          const uint32_t* cnt = tid ? crow : prow;
+          uint32_t nseg = 0, acc = 0;
+          for (uint32_t r = 0; r < nrows; ++r) {
+            if (acc + cnt[r] > lcap) { s.segend[tid][nseg++] = r; acc = 0; }  // a single row always fits (host check)
+            acc += cnt[r];
+          }
+          s.segend[tid][nseg++] = nrows;
+          s.scal[S_NBAND + tid] = nseg;
+        }
+      }
+      RB_SYNC();
+    }
+    const uint32_t nband = fast ? 1u : s.scal[S_NBAND], nchunk = fast ? 1u : s.scal[S_NCHUNK];
+
     bool restart = true;
     while (restart) {
       restart = false;
       gtop[0] = gtop[1] = gtop[2] = 0;
       nbins = 0;
-      RB_FOR_THREADS(tid, NT) {
-        if (tid < 6) s.scal[S_NGT0 + tid] = 0;
-        if (tap && tid == 0) *p.tap_count = 0;
-      }
-      RB_SYNC();
       for (uint32_t sweep = 0; sweep < 2 && !restart; ++sweep) {
         for (uint32_t q = 0; q < Q && !restart; ++q) {
           if (sweep == 0 || Q > 1) {
             // ---- build the offset histogram of partition q ---------------------------------
-            RB_FOR_THREADS(tid, NT) {
-              for (uint32_t i = tid; i < p.off_slots; i += NT) { s.okey[i] = EMPTY; s.ocnt[i] = 0; }
-              if (tid == 0) { s.scal[S_NTOUCHED] = 0; s.scal[S_OVERFLOW] = 0; }
-            }
-            RB_SYNC();
-            uint32_t ra = 0;
-            while (ra < nrows) {
-              // band [ra, rb): as many previous rows as fit the code table
-              uint32_t rb = ra, cnt = 0;
-              while (rb < nrows && cnt + prow[rb] <= code_cap) { cnt += prow[rb]; ++rb; }
-              if (rb == ra) { cnt = prow[rb]; ++rb; }  // a single row always fits (asserted by the host)
-              if (cnt != 0) {
-                uint32_t cslots = 64;
-                while (cslots < 2 * cnt) cslots <<= 1;
-                const uint32_t cmask = cslots - 1;
-                RB_FOR_THREADS(tid, NT) {
-                  for (uint32_t i = tid; i < cslots; i += NT) s.cpos[i] = EMPTY;
+            for (uint32_t band = 0; band < nband; ++band) {
+              const uint32_t ra = (fast || band == 0) ? 0u : s.segend[0][band - 1];
+              const uint32_t rb = fast ? nrows : s.segend[0][band];
+              uint32_t bcnt = eff_prev;
+              if (!fast) { bcnt = 0; for (uint32_t r = ra; r < rb; ++r) bcnt += prow[r]; }
+              uint32_t cslots = 64;
+              while (cslots < 2 * bcnt) cslots <<= 1;
+              const uint32_t cmask = cslots - 1;
+              // phase A: clear tables and fill counters
+              RB_FOR_THREADS(tid, NT) {
+                for (uint32_t i = tid; i < cslots; i += NT) s.ctab[i] = EMPTY;
+                if (band == 0) {
+                  for (uint32_t i = tid; i < p.off_slots; i += NT) { s.okey[i] = EMPTY; s.ocnt[i] = 0; }
+                  if (tid == 0) { s.scal[S_NTOUCHED] = 0; s.scal[S_OVERFLOW] = 0; }
+                  if (tid < 6) s.scal[S_NGT0 + tid] = (sweep == 0) ? 0u : s.scal[S_NGT0 + tid];
+                  if (tid < 3 && sweep == 0) s.best[tid] = 0;
+                  if (tap && tid == 0 && sweep == 0 && q == 0) *p.tap_count = 0;
                 }
-                RB_SYNC();
-                // insert previous keypoints of the band
-                RB_FOR_THREADS(tid, NT) {
-                  for (uint32_t i = tid; i < (rb - ra) * nstr; i += NT) {
-                    const uint32_t row = ra + i / nstr, j = j0 + i % nstr;
-                    uint32_t w = kp_src[((uint64_t)fprev * g.H + (Y0 + row)) * g.NS + j] & RB_COLMASK(j);
-                    while (w) {
-                      const uint32_t b = rb_ffs0(w);
-                      w &= w - 1;
-                      const uint32_t x = RB_STRIP_OUT * j + b, y = Y0 + row;
-                      const Code c = code_at(s.tile[0], p.tile_pitch, x - 2 - tx0, row);
-                      const uint32_t h = code_hash(c);
-                      uint32_t slot = h & cmask;
-                      while (rb_atomic_cas(&s.cpos[slot], EMPTY, (y << 16) | x) != EMPTY) slot = (slot + 1) & cmask;
-                      s.ctag[slot] = h;
-                    }
+                if (tid == 0) { s.scal[S_PFILL] = 0; s.scal[S_CFILL] = 0; }
+              }
+              RB_SYNC();
+              // phase B: compact the band's previous keypoints (and, with a single chunk, the current ones)
+              RB_FOR_THREADS(tid, NT) {
+                const uint32_t nprow = rb - ra;
+                const uint32_t extra = (nchunk == 1 && band == 0) ? nrows : 0u;
+                for (uint32_t i = tid; i < nprow + extra; i += NT) {
+                  if (i < nprow) {
+                    const uint32_t row = ra + i, c = prow[row];
+                    if (c) emit_row(kp_src, kprow_prev + (uint64_t)row * g.NS, j0, nstr, X0, X1, Y0 + row, s.plist,
+                                    rb_atomic_add(&s.scal[S_PFILL], c));
+                  } else {
+                    const uint32_t row = i - nprow, c = crow[row];
+                    if (c) emit_row(kp_src, kprow_curr + (uint64_t)row * g.NS, j0, nstr, X0, X1, Y0 + row, s.clist,
+                                    rb_atomic_add(&s.scal[S_CFILL], c));
                   }
                 }
-                RB_SYNC();
-                // probe with every current keypoint, vote prev - curr
+              }
+              RB_SYNC();
+              // phase C: insert the previous keypoints into the code table
+              RB_FOR_THREADS(tid, NT) {
+                for (uint32_t i = tid; i < bcnt; i += NT) {
+                  const uint32_t pp = s.plist[i];
+                  const Code c = code_at(s.tile[0], p.tile_pitch, (pp & 0xFFFFu) - 2 - tx0, (pp >> 16) - Y0);
+                  const uint32_t h = code_hash(c);
+                  uint32_t slot = h & cmask;
+                  while (rb_atomic_cas(&s.ctab[slot], EMPTY, (h & 0x7FFFF000u) | i) != EMPTY) slot = (slot + 1) & cmask;
+                }
+              }
+              RB_SYNC();
+              for (uint32_t chunk = 0; chunk < nchunk; ++chunk) {
+                uint32_t ccnt = eff_curr;
+                if (nchunk > 1) {
+                  const uint32_t ca = chunk == 0 ? 0u : s.segend[1][chunk - 1], cb = s.segend[1][chunk];
+                  ccnt = 0;
+                  for (uint32_t r = ca; r < cb; ++r) ccnt += crow[r];
+                  RB_FOR_THREADS(tid, NT) {
+                    if (tid == 0) s.scal[S_CFILL] = 0;
+                  }
+                  RB_SYNC();
+                  RB_FOR_THREADS(tid, NT) {
+                    for (uint32_t i = tid; i < cb - ca; i += NT) {
+                      const uint32_t row = ca + i, c = crow[row];
+                      if (c) emit_row(kp_src, kprow_curr + (uint64_t)row * g.NS, j0, nstr, X0, X1, Y0 + row, s.clist,
+                                      rb_atomic_add(&s.scal[S_CFILL], c));
+                    }
+                  }
+                  RB_SYNC();
+                }
+                // phase D: probe with every current keypoint of the chunk, vote prev - curr
                 RB_FOR_THREADS(tid, NT) {
-                  for (uint32_t i = tid; i < nrows * nstr; i += NT) {
-                    const uint32_t row = i / nstr, j = j0 + i % nstr;
-                    uint32_t w = kp_src[((uint64_t)fcurr * g.H + (Y0 + row)) * g.NS + j] & RB_COLMASK(j);
-                    while (w) {
-                      const uint32_t b = rb_ffs0(w);
-                      w &= w - 1;
-                      const uint32_t x = RB_STRIP_OUT * j + b, y = Y0 + row;
-                      const Code c = code_at(s.tile[1], p.tile_pitch, x - 2 - tx0, row);
-                      const uint32_t h = code_hash(c);
-                      uint32_t slot = h & cmask;
-                      uint32_t pp;
-                      while ((pp = s.cpos[slot]) != EMPTY) {
-                        if (s.ctag[slot] == h) {
-                          const uint32_t px = pp & 0xFFFFu, py = pp >> 16;
-                          const Code d = code_at(s.tile[0], p.tile_pitch, px - 2 - tx0, py - Y0);
-                          if (d.c0 == c.c0 && d.c1 == c.c1 && d.c2 == c.c2 && d.c3 == c.c3) {
-                            // offset = prev - curr (src/kpm.hpp:96-98), biased into 16 + 16 bits
-                            const uint32_t key = ((py - y + 32768u) << 16) | ((px - x + 32768u) & 0xFFFFu);
-                            const uint32_t oh = off_hash(key);
-                            if (Q == 1 || (oh >> 12) % Q == q) {
-                              uint32_t os = oh & (p.off_slots - 1);
-                              while (true) {
-                                uint32_t k = s.okey[os];
+                  for (uint32_t i = tid; i < ccnt; i += NT) {
+                    const uint32_t cp = s.clist[i];
+                    const uint32_t x = cp & 0xFFFFu, y = cp >> 16;
+                    const Code c = code_at(s.tile[1], p.tile_pitch, x - 2 - tx0, y - Y0);
+                    const uint32_t h = code_hash(c);
+                    uint32_t slot = h & cmask;
+                    uint32_t e;
+                    while ((e = s.ctab[slot]) != EMPTY) {
+                      if (((e ^ h) & 0x7FFFF000u) == 0) {
+                        const uint32_t pp = s.plist[e & 0xFFFu];
+                        const uint32_t px = pp & 0xFFFFu, py = pp >> 16;
+                        const Code d = code_at(s.tile[0], p.tile_pitch, px - 2 - tx0, py - Y0);
+                        if (d.c0 == c.c0 && d.c1 == c.c1 && d.c2 == c.c2 && d.c3 == c.c3) {
+                          // offset = prev - curr (src/kpm.hpp:96-98), biased into 16 + 16 bits
+                          const uint32_t key = ((py - y + 32768u) << 16) | ((px - x + 32768u) & 0xFFFFu);
+                          const uint32_t oh = off_hash(key);
+                          if (Q == 1 || (oh >> 12) % Q == q) {
+                            uint32_t os = oh & (p.off_slots - 1);
+                            while (true) {
+                              uint32_t k = s.okey[os];
+                              if (k == EMPTY) {
+                                if (rb_volatile_load(&s.scal[S_NTOUCHED]) >= off_cap) { s.scal[S_OVERFLOW] = 1; break; }
+                                k = rb_atomic_cas(&s.okey[os], EMPTY, key);
                                 if (k == EMPTY) {
-                                  if (rb_volatile_load(&s.scal[S_NTOUCHED]) >= off_cap) { s.scal[S_OVERFLOW] = 1; break; }
-                                  k = rb_atomic_cas(&s.okey[os], EMPTY, key);
-                                  if (k == EMPTY) {
-                                    const uint32_t t = rb_atomic_add(&s.scal[S_NTOUCHED], 1);
-                                    s.touched[t] = os;
-                                    k = key;
-                                  }
+                                  const uint32_t t = rb_atomic_add(&s.scal[S_NTOUCHED], 1);
+                                  s.touched[t] = os;
+                                  k = key;
                                 }
-                                if (k == key) { rb_atomic_add(&s.ocnt[os], 1); break; }
-                                os = (os + 1) & (p.off_slots - 1);
                               }
+                              if (k == key) { rb_atomic_add(&s.ocnt[os], 1); break; }
+                              os = (os + 1) & (p.off_slots - 1);
                             }
                           }
                         }
-                        slot = (slot + 1) & cmask;
                       }
+                      slot = (slot + 1) & cmask;
                     }
                   }
                 }
                 RB_SYNC();
               }
-              ra = rb;
             }
             if (s.scal[S_OVERFLOW] != 0) {  // block-uniform: read after the barrier
               Q *= 4;
@@ -346,10 +426,6 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
             unsigned long long ptop[3] = {0, 0, 0};
             for (uint32_t round = 0; round < rv; ++round) {
               RB_FOR_THREADS(tid, NT) {
-                if (tid == 0) s.best[round] = 0;
-              }
-              RB_SYNC();
-              RB_FOR_THREADS(tid, NT) {
                 unsigned long long loc = 0;
                 for (uint32_t i = tid; i < nt; i += NT) {
                   const uint32_t os = s.touched[i];
@@ -363,6 +439,7 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
               below = ptop[round];
               if (below == 0) break;
             }
+            if (Q > 1) RB_SYNC();  // best[] is reset by the next partition's phase A
             // merge into the running top (uniform, registers only)
             for (uint32_t a = 0; a < rv; ++a) {
               unsigned long long v = ptop[a];
@@ -392,7 +469,6 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
       }
     }
   }
-#undef RB_COLMASK
 
   // ---- write the region's ballot ---------------------------------------------------------------
   RB_FOR_THREADS(tid, NT) {
