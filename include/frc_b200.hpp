@@ -1,0 +1,248 @@
+// frc_b200.hpp -- a frc::collector-shaped front of the B200 registration path.
+//
+// Drop-in for the reference's frame collector (src/frc.hpp:27-143): same constructor, same
+// collect(feed, comp, cb) / current() / complete() surface, same callback contract
+// (cb(fragment, frame, median, keys), src/frc.hpp:119), same result (the fragment list with every
+// frame blitted at its accumulated position).  mpb::builder::collect (src/mpb.hpp:52-61) switches by
+// naming frc_b200::collector instead of frc::collector; see INTEGRATION.md.
+//
+// What moves to the GPU: kpe::extractor::extract (src/frc.hpp:90,105) and kpm::match (src/frc.hpp:107)
+// for a whole BATCH of frames per call, through the C ABI of remap_b200.h.  What stays here, in the
+// reference's own types and order: feed.produce, position_ += off / add_fragment
+// (src/frc.hpp:108-115,124-127), fragment::blit with the compressed image + median (:129-135), the
+// callback.  This header is compiled in the REFERENCE's translation unit, so it includes the
+// reference headers by the names the reference uses; it contains no CUDA.
+//
+// Differences a caller can observe (both documented in INTEGRATION.md):
+//  * frames are pulled from the feeder `batch` at a time before the first callback of the batch;
+//  * `keys` handed to the callback is populated only when `fill_keys` is set (the reference's only
+//    callback ignores it, src/main.cpp:139-149); populating costs one device round trip per frame.
+#pragma once
+
+#include "remap_b200.h"
+
+#include "fgm.hpp"
+#include "ifd.hpp"
+#include "kpr.hpp"
+
+#include <cstring>
+#include <list>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace frc_b200 {
+
+template<typename Ty>
+using allocator_t = all::frame_allocator<Ty>;
+
+using image_type = sid::nat::aimg_t<allocator_t<cpl::nat_cc>>;
+using frame_type = ifd::frame<image_type>;
+
+// src/frc.hpp:22-24
+static inline constexpr std::size_t grid_horizontal{4};
+static inline constexpr std::size_t grid_vertical{2};
+static inline constexpr std::size_t grid_overlap{16};
+
+using grid_type = kpr::grid<grid_horizontal, grid_vertical, allocator_t<char>>;
+
+struct options {
+  std::size_t batch{2048};  // frames registered per rb_register call
+  int device{0};
+  bool fill_keys{false};    // rebuild the kpr::grid for the callback from rb_keypoints
+};
+
+class collector {
+  using pixel_alloc_t = allocator_t<cpl::nat_cc>;
+
+public:
+  explicit collector(mrl::dimensions_t dimensions, options opt = {})
+      : dimensions_{dimensions}
+      , opt_{opt} {
+    if (opt_.batch < 2) {
+      opt_.batch = 2;
+    }
+
+    rb_config cfg;
+    rb_default_config(&cfg,
+                      static_cast<std::uint32_t>(dimensions.width_),
+                      static_cast<std::uint32_t>(dimensions.height_),
+                      static_cast<std::uint32_t>(opt_.batch + 1));
+    cfg.grid_w = grid_horizontal;
+    cfg.grid_h = grid_vertical;
+    cfg.overlap = grid_overlap;
+    cfg.weight_switch = 10; // frc::collector::match_config, src/frc.hpp:32
+    cfg.region_votes = 3;   // src/frc.hpp:33
+    cfg.device = opt_.device;
+
+    if (auto rc{rb_create(&cfg, &ctx_)}; rc != RB_OK) {
+      std::string msg{ctx_ != nullptr ? rb_last_error(ctx_) : "no CUDA device"};
+      rb_destroy(ctx_);
+      ctx_ = nullptr;
+      throw std::runtime_error("frc_b200::collector: " + msg);
+    }
+
+    auto pixels{dimensions.area()};
+    stage_ = static_cast<std::uint8_t*>(rb_alloc_host((opt_.batch + 1) * pixels));
+    medians_ = static_cast<std::uint8_t*>(rb_alloc_host((opt_.batch + 1) * pixels));
+    offsets_ = static_cast<rb_offset*>(rb_alloc_host((opt_.batch + 1) * sizeof(rb_offset)));
+    if (stage_ == nullptr || medians_ == nullptr || offsets_ == nullptr) {
+      release();
+      throw std::runtime_error("frc_b200::collector: pinned host allocation failed");
+    }
+  }
+
+  collector(collector const&) = delete;
+  collector& operator=(collector const&) = delete;
+
+  ~collector() {
+    release();
+  }
+
+  template<typename Feeder, typename Comp, typename Callback>
+  void collect(Feeder&& feed, Comp&& comp, Callback&& cb) requires(
+      ifd::feeder<std::decay_t<Feeder>, pixel_alloc_t>&&
+          icd::compressor<std::decay_t<Comp>, pixel_alloc_t>) {
+    if (!feed.has_more()) {
+      return;
+    }
+
+    auto pixels{dimensions_.area()};
+    all::memory_stack<cpl::nat_cc> memory{};
+    bool first_batch{true};
+
+    while (feed.has_more()) {
+      // one pool per batch; the previous batch's pool stays alive (two-pool swing, src/all.hpp:151-205)
+      all::memory_swing swing{memory};
+      pixel_alloc_t alloc{swing};
+
+      std::vector<frame_type> frames;
+      frames.reserve(opt_.batch);
+      while (frames.size() < opt_.batch && feed.has_more()) {
+        frames.push_back(feed.produce(alloc));
+      }
+
+      // slot 0 of the device frame store = last frame of the previous batch (the `previous` grid
+      // of src/frc.hpp:64-65); slots 1.. = this batch
+      auto base{first_batch ? std::size_t{0} : std::size_t{1}};
+      if (!first_batch) {
+        std::memcpy(stage_, carry_.data(), pixels);
+      }
+      for (std::size_t i{0}; i < frames.size(); ++i) {
+        std::memcpy(stage_ + (base + i) * pixels, frames[i].image_.data(), pixels);
+      }
+
+      auto total{base + frames.size()};
+      check(rb_upload(ctx_, stage_, 0, total));
+      check(rb_register(ctx_, 0, total, offsets_, medians_));
+
+      for (std::size_t i{0}; i < frames.size(); ++i) {
+        auto& frame{frames[i]};
+        auto& dim{frame.image_.dimensions()};
+
+        image_type median{dim, alloc};
+        std::memcpy(median.data(), medians_ + (base + i) * pixels, pixels);
+
+        bool init{first_batch && i == 0};
+        if (init) {
+          add_fragment(dim); // process_init, src/frc.hpp:83-95
+        }
+        else {
+          auto const& off{offsets_[base + i - 1]};
+          if ((off.flags & RB_OFFSET_VALID) != 0) {
+            position_.x_ += off.dx; // src/frc.hpp:108-111
+            position_.y_ += off.dy;
+          }
+          else {
+            add_fragment(dim); // src/frc.hpp:113-115
+          }
+        }
+
+        auto& [no, image]{frame};
+        current_->blit(position_, image, {comp(image), comp(median)}, no); // src/frc.hpp:129-135
+
+        if (!init) { // the reference does not call back for the first frame (src/frc.hpp:83-95)
+          grid_type keys{allocator_t<char>{alloc}};
+          if (opt_.fill_keys) {
+            fill(keys, base + i);
+          }
+          cb(*current_, frame, median, keys);
+        }
+      }
+
+      auto last{frames.back().image_.data()};
+      carry_.assign(reinterpret_cast<std::uint8_t const*>(last),
+                    reinterpret_cast<std::uint8_t const*>(last) + pixels);
+      first_batch = false;
+    }
+  }
+
+  [[nodiscard]] inline fgm::fragment const& current() const noexcept {
+    return *current_;
+  }
+
+  [[nodiscard]] inline std::list<fgm::fragment> complete() noexcept {
+    for (auto& fragment : fragments_) {
+      fragment.normalize();
+    }
+
+    return std::move(fragments_);
+  }
+
+private:
+  inline void add_fragment(mrl::dimensions_t dimension) {
+    current_ = &fragments_.emplace_back(dimension);
+    position_.x_ = position_.y_ = 0;
+  }
+
+  // kpr::grid as kpe::extractor would have filled it (src/kpe.hpp:225-229,301-303)
+  void fill(grid_type& keys, std::size_t slot) {
+    kps_.resize(dimensions_.area());
+    std::size_t count{0};
+    check(rb_keypoints(ctx_, slot, kps_.data(), kps_.size(), &count));
+    for (std::size_t k{0}; k < count; ++k) {
+      auto const& kp{kps_[k]};
+      kpr::code code;
+      std::memcpy(code.data(), kp.code, sizeof(kp.code));
+      for (std::size_t r{0}; r < grid_type::region_count; ++r) {
+        if ((kp.region_mask >> r) & 1u) {
+          keys[r].add(code, mrl::point_t{kp.x, kp.y});
+        }
+      }
+    }
+  }
+
+  void check(int rc) {
+    if (rc != RB_OK) {
+      throw std::runtime_error(std::string{"frc_b200::collector: "} + rb_last_error(ctx_));
+    }
+  }
+
+  void release() noexcept {
+    rb_free_host(stage_);
+    rb_free_host(medians_);
+    rb_free_host(offsets_);
+    stage_ = medians_ = nullptr;
+    offsets_ = nullptr;
+    rb_destroy(ctx_);
+    ctx_ = nullptr;
+  }
+
+private:
+  mrl::dimensions_t dimensions_;
+  options opt_;
+
+  rb_ctx* ctx_{nullptr};
+  std::uint8_t* stage_{nullptr};
+  std::uint8_t* medians_{nullptr};
+  rb_offset* offsets_{nullptr};
+  std::vector<std::uint8_t> carry_;
+  std::vector<rb_keypoint> kps_;
+
+  fgm::point_t position_{};
+
+  std::list<fgm::fragment> fragments_;
+  fgm::fragment* current_{nullptr};
+};
+
+} // namespace frc_b200

@@ -137,6 +137,12 @@ const rb_offset* rb_offsets_device(rb_ctx* ctx);
 /* Number of keypoints (unique pixels, not region insertions) K1 found in frames [first, first+n). */
 int rb_count_keypoints(rb_ctx* ctx, size_t first, size_t n, uint64_t* total);
 
+/* Page-locked host memory for the caller's staging buffers (frames in, offsets / medians out): with
+ * pinned buffers rb_upload and the fetches are true asynchronous DMA.  Plain malloc'ed memory works
+ * too, only slower.  (The reference allocates frames from all::memory_pool, src/all.hpp:14-106.) */
+void* rb_alloc_host(size_t bytes);
+void rb_free_host(void* p);
+
 /* Introspection for benchmarks and tests. */
 int rb_synchronize(rb_ctx* ctx);
 void* rb_stream(rb_ctx* ctx);                          /* the cudaStream_t the kernels run on       */

@@ -28,6 +28,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = os.environ.get("REMAP_REFERENCE_SRC", "/root/reference/src")
 OUT_DIR = os.path.join(HERE, "_ref")
 OUT_BIN = os.path.join(OUT_DIR, "ref_harness")
+SHIM_BIN = os.path.join(OUT_DIR, "shim_harness")
+REPO = os.path.dirname(HERE)
 
 # (file, old, new, expected_count) -- semantics-preserving MSVC->GCC fixes only.
 PATCHES = [
@@ -77,6 +79,33 @@ def patched_tree(dst):
         f.write("#pragma once\n#include <immintrin.h>\n")
 
 
+def build_shim(verbose=True):
+    """oracle/_ref/shim_harness: the reference's frc::collector next to include/frc_b200.hpp (the
+    collector-shaped front of the C ABI), linked against remap_b200/libremap_b200.so.  Returns the
+    binary's path, or None if it cannot be had (no reference sources and no prebuilt binary)."""
+    lib = os.path.join(REPO, "remap_b200", "libremap_b200.so")
+    if not os.path.isdir(REF_SRC) or not os.path.exists(lib):
+        return SHIM_BIN if os.path.exists(SHIM_BIN) else None
+    harness = os.path.join(HERE, "shim_harness.cpp")
+    srcs = [harness, os.path.join(REPO, "include", "frc_b200.hpp"), os.path.join(REPO, "include", "remap_b200.h"),
+            __file__]
+    if os.path.exists(SHIM_BIN) and os.path.getmtime(SHIM_BIN) >= max(os.path.getmtime(p) for p in srcs):
+        return SHIM_BIN
+    os.makedirs(OUT_DIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="remap_ref_")
+    try:
+        patched_tree(tmp)
+        cmd = (["g++"] + CXXFLAGS + ["-I", tmp, "-I", os.path.join(REPO, "include"), harness, "-o", SHIM_BIN,
+                                     "-L", os.path.dirname(lib), "-lremap_b200",
+                                     "-Wl,-rpath,$ORIGIN/../../remap_b200"])
+        if verbose:
+            print("[oracle/_ref]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return SHIM_BIN
+
+
 def build(verbose=True):
     """Returns the path of the harness binary, or None if it cannot be had."""
     if not os.path.isdir(REF_SRC):
@@ -100,5 +129,6 @@ def build(verbose=True):
 
 if __name__ == "__main__":
     p = build()
+    print(build_shim())
     print(p if p else "reference sources not available and no prebuilt oracle/_ref")
     sys.exit(0 if p else 1)

@@ -1,0 +1,190 @@
+// oracle/shim_harness.cpp -- drop-in check of include/frc_b200.hpp against the REAL frc::collector.
+//
+// TEST INFRASTRUCTURE ONLY (built by oracle/build_ref.py into oracle/_ref/shim_harness, which links
+// remap_b200/libremap_b200.so).  This file is ours.  It includes the reference's own headers
+// (patched for GCC in a temp dir at build time), runs the same frame sequence through
+//   frc::collector::collect        (src/frc.hpp:55-68)   -- the reference, CPU
+//   frc_b200::collector::collect   (include/frc_b200.hpp) -- the C-ABI / B200 path
+// with the reference's feeder concept (src/ifd.hpp:20-28), the reference's nic::compress
+// (src/nic.hpp:8-105) as the compressor and a recording callback, and compares everything the rest
+// of the pipeline (mpb/fgs/fdf) can observe of the result:
+//   fragment count; per fragment: zero, dots dimensions, every dot histogram, and per frame its
+//   number, position and the compressed image + compressed MEDIAN bytes; the callback sequence;
+//   and (fill_keys = 1) the kpr::grid contents handed to the callback.
+//
+// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1>     exit 0 = identical
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "frc.hpp"
+#include "nic.hpp"
+
+#include "frc_b200.hpp"
+
+namespace {
+
+std::vector<std::uint8_t> read_file(char const* path, std::size_t expect) {
+  std::vector<std::uint8_t> buf(expect);
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { std::fprintf(stderr, "cannot open %s\n", path); std::exit(2); }
+  std::size_t got = std::fread(buf.data(), 1, expect, f);
+  std::fclose(f);
+  if (got != expect) { std::fprintf(stderr, "%s: short read\n", path); std::exit(2); }
+  return buf;
+}
+
+class memory_feed {  // models ifd::feeder
+public:
+  memory_feed(std::uint8_t const* data, std::size_t w, std::size_t h, std::size_t n)
+      : data_{data}, dim_{w, h}, last_{n} {}
+  [[nodiscard]] bool has_more() const noexcept { return next_ < last_; }
+  template<typename Alloc>
+  [[nodiscard]] auto produce(Alloc const& alloc) {
+    using image_type = sid::nat::aimg_t<Alloc>;
+    image_type img{dim_, alloc};
+    std::memcpy(img.data(), data_ + next_ * dim_.area(), dim_.area());
+    return ifd::frame<image_type>{next_++, std::move(img)};
+  }
+private:
+  std::uint8_t const* data_;
+  mrl::dimensions_t dim_;
+  std::size_t next_{0}, last_;
+};
+
+struct native_compression {  // what main.cpp plugs in (src/main.cpp:112-125)
+  template<typename Alloc>
+  [[nodiscard]] icd::compressed_t operator()(sid::nat::aimg_t<Alloc> const& image) const {
+    return nic::compress(image);
+  }
+};
+
+struct key_rec {
+  std::uint32_t region; std::uint16_t x, y; std::uint8_t code[13];
+  bool operator<(key_rec const& o) const { return std::memcmp(this, &o, sizeof(*this)) < 0; }
+  bool operator==(key_rec const& o) const { return std::memcmp(this, &o, sizeof(*this)) == 0; }
+};
+
+struct call_rec {
+  std::size_t frame_no;
+  std::size_t fragment_frames;  // frames blitted into the current fragment when called
+  std::vector<std::uint8_t> median;
+  std::vector<key_rec> keys;
+  std::vector<std::size_t> weights;
+};
+
+struct recorder {
+  std::vector<call_rec>* calls;
+  bool keep_keys;
+  template<typename Frame, typename Image, typename Grid>
+  void operator()(fgm::fragment const& frag, Frame const& frame, Image const& median, Grid const& keys) {
+    call_rec r;
+    r.frame_no = frame.number_;
+    r.fragment_frames = frag.frames().size();
+    r.median.assign(reinterpret_cast<std::uint8_t const*>(median.data()),
+                    reinterpret_cast<std::uint8_t const*>(median.end()));
+    if (keep_keys) {
+      std::uint32_t ri = 0;
+      for (auto& region : keys.regions()) {
+        for (auto& [code, pts] : region.points())
+          for (auto& p : pts) {
+            key_rec k;
+            std::memset(&k, 0, sizeof(k));
+            k.region = ri; k.x = static_cast<std::uint16_t>(p.x_); k.y = static_cast<std::uint16_t>(p.y_);
+            std::memcpy(k.code, code.data(), 13);
+            r.keys.push_back(k);
+          }
+        r.weights.push_back(region.counts()[1]);
+        r.weights.push_back(region.counts()[2]);
+        ++ri;
+      }
+      std::sort(r.keys.begin(), r.keys.end());
+    }
+    calls->push_back(std::move(r));
+  }
+};
+
+int fail(char const* what, std::size_t a = 0, std::size_t b = 0) {
+  std::printf("MISMATCH: %s (%zu, %zu)\n", what, a, b);
+  return 1;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  if (argc < 7) { std::fprintf(stderr, "usage: shim_harness frames.bin W H N batch fill_keys\n"); return 2; }
+  std::size_t const w = std::strtoul(argv[2], nullptr, 10), h = std::strtoul(argv[3], nullptr, 10);
+  std::size_t const n = std::strtoul(argv[4], nullptr, 10), batch = std::strtoul(argv[5], nullptr, 10);
+  bool const fill = std::atoi(argv[6]) != 0;
+  auto data = read_file(argv[1], w * h * n);
+
+  std::vector<call_rec> ref_calls, gpu_calls;
+  std::list<fgm::fragment> ref_frags, gpu_frags;
+
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    frc::collector collector{mrl::dimensions_t{w, h}};
+    memory_feed feed{data.data(), w, h, n};
+    collector.collect(feed, native_compression{}, recorder{&ref_calls, fill});
+    ref_frags = collector.complete();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  {
+    frc_b200::options opt;
+    opt.batch = batch;
+    opt.fill_keys = fill;
+    frc_b200::collector collector{mrl::dimensions_t{w, h}, opt};
+    memory_feed feed{data.data(), w, h, n};
+    collector.collect(feed, native_compression{}, recorder{&gpu_calls, fill});
+    gpu_frags = collector.complete();
+  }
+  auto t2 = std::chrono::steady_clock::now();
+
+  if (ref_frags.size() != gpu_frags.size()) return fail("fragment count", ref_frags.size(), gpu_frags.size());
+  auto gi = gpu_frags.begin();
+  std::size_t fi = 0, nframes = 0;
+  for (auto& rf : ref_frags) {
+    auto& gf = *gi++;
+    if (!(rf.zero() == gf.zero())) return fail("fragment zero", fi);
+    if (rf.dots().width() != gf.dots().width() || rf.dots().height() != gf.dots().height())
+      return fail("fragment dimensions", fi);
+    if (std::memcmp(rf.dots().data(), gf.dots().data(), rf.dots().size() * sizeof(fgm::dot_type)) != 0)
+      return fail("fragment dots", fi);
+    if (rf.frames().size() != gf.frames().size()) return fail("fragment frame count", fi);
+    for (std::size_t k = 0; k < rf.frames().size(); ++k) {
+      auto& a = rf.frames()[k];
+      auto& b = gf.frames()[k];
+      if (a.number_ != b.number_) return fail("frame number", fi, k);
+      if (!(a.position_ == b.position_)) return fail("frame position", fi, k);
+      if (a.data_.image_ != b.data_.image_) return fail("compressed image", fi, k);
+      if (a.data_.median_ != b.data_.median_) return fail("compressed median", fi, k);
+      ++nframes;
+    }
+    ++fi;
+  }
+  if (ref_calls.size() != gpu_calls.size()) return fail("callback count", ref_calls.size(), gpu_calls.size());
+  for (std::size_t k = 0; k < ref_calls.size(); ++k) {
+    auto& a = ref_calls[k];
+    auto& b = gpu_calls[k];
+    if (a.frame_no != b.frame_no) return fail("callback frame", k);
+    if (a.fragment_frames != b.fragment_frames) return fail("callback fragment state", k);
+    if (a.median != b.median) return fail("callback median", k);
+    if (fill && !(a.keys == b.keys)) return fail("callback keys", k, a.keys.size());
+    if (fill && a.weights != b.weights) return fail("callback weight counts", k);
+  }
+  std::printf("IDENTICAL: %zu fragments, %zu frames, %zu callbacks%s; reference %.1f ms, frc_b200 %.1f ms\n",
+              ref_frags.size(), nframes, ref_calls.size(), fill ? " (keys compared)" : "",
+              std::chrono::duration<double, std::milli>(t1 - t0).count(),
+              std::chrono::duration<double, std::milli>(t2 - t1).count());
+  return 0;
+}

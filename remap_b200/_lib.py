@@ -22,7 +22,7 @@ SYMBOLS = [
     "rb_fetch_medians", "rb_register", "rb_keypoints", "rb_region_ballots", "rb_region_votes",
     "rb_foreground_mask", "rb_foreground_mask_resident", "rb_synchronize", "rb_stream", "rb_kernel_times",
     "rb_kernel_launches", "rb_device_bytes", "rb_last_error", "rb_abi_version", "rb_offsets_device",
-    "rb_count_keypoints",
+    "rb_count_keypoints", "rb_alloc_host", "rb_free_host",
 ]
 
 
@@ -98,6 +98,10 @@ def load(build_if_missing: bool = False):
     lib.rb_offsets_device.argtypes = [vp]
     lib.rb_count_keypoints.restype = C.c_int
     lib.rb_count_keypoints.argtypes = [vp, sz, sz, C.POINTER(C.c_uint64)]
+    lib.rb_alloc_host.restype = vp
+    lib.rb_alloc_host.argtypes = [sz]
+    lib.rb_free_host.restype = None
+    lib.rb_free_host.argtypes = [vp]
     lib.rb_abi_version.restype = u32
     lib.rb_abi_version.argtypes = []
     _lib = lib

@@ -334,6 +334,15 @@ void* rb_stream(rb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr;
 uint64_t rb_kernel_launches(rb_ctx* c) { return c ? c->launches : 0; }
 size_t rb_device_bytes(rb_ctx* c) { return c ? c->bytes : 0; }
 
+void* rb_alloc_host(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void rb_free_host(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int rb_synchronize(rb_ctx* c) {
   if (!c) return RB_ERR_INVALID;
   RB_CUDA(c, cudaSetDevice(c->device));

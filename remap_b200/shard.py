@@ -23,7 +23,7 @@ def shard_range(n_frames: int, world: int, rank: int):
     (pair i = frames (i, i+1))."""
     lo = rank * n_frames // world
     hi = (rank + 1) * n_frames // world
-    first = lo - 1 if rank > 0 else 0
+    first = lo - 1 if lo > 0 else 0   # ranks whose predecessors are all empty start the sequence
     if hi <= lo:
         return lo, lo, max(lo - 1, 0), max(lo - 1, 0)
     return first, hi, first, hi - 1

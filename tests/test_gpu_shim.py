@@ -1,0 +1,50 @@
+"""-m gpu: the collector-shaped C++ front of the C ABI (include/frc_b200.hpp) is a drop-in for the
+reference's frc::collector.  oracle/_ref/shim_harness (built by oracle/build_ref.py from the
+reference's own headers + our header, linked against libremap_b200.so) runs both collectors on
+the same frames with the reference's feeder concept, nic::compress and a recording callback and
+compares fragments, dot histograms, frame positions, compressed images AND compressed medians, the
+callback sequence, and (fill_keys) the kpr::grid handed to the callback."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from remap_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(frames, batch, fill, tmp_path):
+    if not os.path.exists(SHIM):
+        pytest.fail("oracle/_ref/shim_harness missing: run `python oracle/build_ref.py` in the build container")
+    n, H, W = frames.shape
+    path = os.path.join(tmp_path, "frames.bin")
+    np.ascontiguousarray(frames, np.uint8).tofile(path)
+    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill))], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
+    assert r.stdout.startswith("IDENTICAL"), r.stdout
+    return r.stdout
+
+
+@pytest.mark.parametrize("batch", [2, 7, 64])
+def test_collector_shim_matches_reference_collector(batch, tmp_path):
+    seq = synth.scrolling_tilemap(40, 320, 224, seed=11)
+    out = _run(seq.frames, batch, True, str(tmp_path))
+    assert "1 fragments, 40 frames, 39 callbacks" in out, out
+
+
+def test_collector_shim_scene_cuts_open_fragments(tmp_path):
+    seq = synth.scrolling_tilemap(60, 320, 224, seed=5, cut_every=17)
+    out = _run(seq.frames, 16, False, str(tmp_path))
+    nfrag = int(out.split()[1])
+    assert nfrag >= 2 and "60 frames" in out, out
+
+
+def test_collector_shim_odd_size_and_long_run(tmp_path):
+    seq = synth.scrolling_tilemap(300, 323, 227, seed=9)
+    _run(seq.frames, 128, False, str(tmp_path))
