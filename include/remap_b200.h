@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 1
+#define RB_ABI_VERSION 2
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -54,6 +54,11 @@ typedef struct rb_config {
   uint32_t offset_slots;    /* 0 = auto; shared-memory offset table slots (power of two)   */
   uint32_t profile;         /* 1: record CUDA events around every kernel (rb_kernel_times) */
   void* stream;             /* cudaStream_t to use, or NULL to create one                  */
+  uint32_t kpm_mode;        /* 0 = pipelined matcher, general kernel for what it defers;
+                               1 = general kernel only (one CTA per pair and region)         */
+  uint32_t list_cap;        /* 0 = auto; per-region keypoint list capacity of the pipelined
+                               matcher (<= 2047); longer lists are deferred                   */
+  uint32_t run_pairs;       /* 0 = auto; consecutive pairs per work item of the matcher      */
 } rb_config;
 
 /* == std::optional<cdt::offset_t> returned by kpm::match (src/kpm.hpp:395-415), plus flags. */
@@ -148,6 +153,9 @@ int rb_synchronize(rb_ctx* ctx);
 void* rb_stream(rb_ctx* ctx);                          /* the cudaStream_t the kernels run on       */
 int rb_kernel_times(rb_ctx* ctx, float* ms, size_t n); /* last rb_register_async: kpe, kpm, declare */
 uint64_t rb_kernel_launches(rb_ctx* ctx);              /* kernels launched by this context so far   */
+/* (pair, region) ballots of the last rb_register_async that the pipelined matcher deferred to the
+ * general kernel (waits for the stream). */
+int rb_deferred_count(rb_ctx* ctx, uint32_t* count);
 size_t rb_device_bytes(rb_ctx* ctx);                   /* HBM held by this context                  */
 const char* rb_last_error(rb_ctx* ctx);
 uint32_t rb_abi_version(void);

@@ -22,7 +22,7 @@ SYMBOLS = [
     "rb_fetch_medians", "rb_register", "rb_keypoints", "rb_region_ballots", "rb_region_votes",
     "rb_foreground_mask", "rb_foreground_mask_resident", "rb_synchronize", "rb_stream", "rb_kernel_times",
     "rb_kernel_launches", "rb_device_bytes", "rb_last_error", "rb_abi_version", "rb_offsets_device",
-    "rb_count_keypoints", "rb_alloc_host", "rb_free_host",
+    "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count",
 ]
 
 
@@ -31,7 +31,8 @@ class RbConfig(C.Structure):
                 ("overlap", C.c_uint32), ("weight_switch", C.c_uint32), ("region_votes", C.c_uint32),
                 ("device", C.c_int32), ("max_frames", C.c_uint32), ("compute_median", C.c_uint32),
                 ("code_slots", C.c_uint32), ("offset_slots", C.c_uint32), ("profile", C.c_uint32),
-                ("stream", C.c_void_p)]
+                ("stream", C.c_void_p), ("kpm_mode", C.c_uint32), ("list_cap", C.c_uint32),
+                ("run_pairs", C.c_uint32)]
 
 
 class RemapLibraryMissing(RuntimeError):
@@ -98,6 +99,8 @@ def load(build_if_missing: bool = False):
     lib.rb_offsets_device.argtypes = [vp]
     lib.rb_count_keypoints.restype = C.c_int
     lib.rb_count_keypoints.argtypes = [vp, sz, sz, C.POINTER(C.c_uint64)]
+    lib.rb_deferred_count.restype = C.c_int
+    lib.rb_deferred_count.argtypes = [vp, C.POINTER(u32)]
     lib.rb_alloc_host.restype = vp
     lib.rb_alloc_host.argtypes = [sz]
     lib.rb_free_host.restype = None

@@ -35,7 +35,8 @@ class Registrar:
     """
 
     def __init__(self, width, height, max_frames, device=0, compute_median=True, profile=False, stream=None,
-                 code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3):
+                 code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3,
+                 kpm_mode=0, list_cap=0, run_pairs=0):
         self._lib = _lib.load()
         cfg = _lib.RbConfig()
         self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
@@ -46,6 +47,7 @@ class Registrar:
         cfg.profile = int(bool(profile))
         cfg.code_slots, cfg.offset_slots = code_slots, offset_slots
         cfg.stream = stream
+        cfg.kpm_mode, cfg.list_cap, cfg.run_pairs = kpm_mode, list_cap, run_pairs
         self.width, self.height, self.max_frames = width, height, max_frames
         self.nreg = grid[0] * grid[1]
         self._ctx = C.c_void_p()
@@ -170,6 +172,13 @@ class Registrar:
         t = C.c_uint64()
         self._check(self._lib.rb_count_keypoints(self._ctx, first, n, C.byref(t)))
         return int(t.value)
+
+    @property
+    def deferred_count(self):
+        """(pair, region) ballots the pipelined matcher handed to the general kernel in the last register."""
+        n = C.c_uint32()
+        self._check(self._lib.rb_deferred_count(self._ctx, C.byref(n)))
+        return int(n.value)
 
     @property
     def kernel_launches(self):

@@ -14,6 +14,8 @@
 #include "rb_host.hpp"
 #include "rb_kpe.cuh"
 #include "rb_kpm.cuh"
+#include "rb_kpm_fast.cuh"
+#include "rb_prep.cuh"
 
 static_assert(sizeof(rb_region_vote) == sizeof(RbRegionVote), "ABI mirror of RbRegionVote");
 static_assert(sizeof(rb_bin) == sizeof(RbBin), "ABI mirror of RbBin");
@@ -140,6 +142,19 @@ __global__ void rb_count_kernel(const uint32_t* __restrict__ bits, size_t nwords
   if ((threadIdx.x & 31) == 0 && loc) atomicAdd(total, loc);
 }
 
+// The general matcher (rb_kpm.cuh) over the (pair, region) list the pipelined matcher deferred.
+__global__ void __launch_bounds__(256) rb_kpm_deferred_kernel(const RbKpmParams p, const uint2* __restrict__ list,
+                                                              const uint32_t* __restrict__ count, uint32_t cap) {
+  extern __shared__ __align__(16) uint32_t rb_kpm_smem[];
+  uint32_t n = *count;
+  if (n > cap) n = cap;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint2 it = list[i];
+    rbm::kpm_block(p, it.x, it.y, rb_kpm_smem, blockDim.x);
+    __syncthreads();
+  }
+}
+
 // ---- context ------------------------------------------------------------------------------------
 
 struct rb_ctx {
@@ -150,6 +165,17 @@ struct rb_ctx {
   cudaStream_t stream;
   bool own_stream;
   uint8_t* d_frames;
+  uint8_t* d_frames4;    // packed 4 bit/pixel copy of the frame store (K0), read by the pipelined matcher
+  uint32_t pitch4;
+  uint64_t frame_stride4;
+  uint32_t* d_lists;     // [frame][region][list_cap] keypoint positions (K1c)
+  uint2* d_counts;       // [frame][region] (n_all, n_w2)
+  uint2* d_deferred;     // [pair][region] worst case
+  uint32_t* d_work;      // [0] work-item counter, [1] deferred count
+  CUtensorMap tmap;      // 3-D tensor map of d_frames4: (row bytes, rows, frames)
+  RbKpmFastParams fast;  // geometry-dependent constants of the pipelined matcher
+  size_t fast_smem;
+  int fast_ctas_per_sm;
   uint8_t* d_median;
   uint32_t* d_kp;
   uint32_t* d_w2;
@@ -170,6 +196,7 @@ struct rb_ctx {
   size_t reg_first, reg_n;
   cudaEvent_t ev[4];
   uint64_t launches;
+  bool debug_sync;
   std::string err;
 };
 
@@ -178,6 +205,18 @@ struct rb_ctx {
     cudaError_t e_ = (call);                                                                    \
     if (e_ != cudaSuccess) {                                                                    \
       (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      return RB_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+// RB_DEBUG_SYNC=1 in the environment: wait after every launch so that a device fault names its kernel.
+#define RB_LAUNCHED(ctx, name)                                                                  \
+  do {                                                                                          \
+    ++(ctx)->launches;                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                                        \
+    if (e_ == cudaSuccess && (ctx)->debug_sync) e_ = cudaStreamSynchronize((ctx)->stream);      \
+    if (e_ != cudaSuccess) {                                                                    \
+      (ctx)->err = std::string(name) + ": " + cudaGetErrorString(e_);                           \
       return RB_ERR_CUDA;                                                                       \
     }                                                                                           \
   } while (0)
@@ -225,6 +264,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   if (!c) return RB_ERR_INVALID;
   c->cfg = *cfg;
   c->device = cfg->device;
+  c->debug_sync = getenv("RB_DEBUG_SYNC") != nullptr;
   *out = c;  // returned even on failure so that rb_last_error can be read; caller rb_destroy()s it
   if (cfg->max_frames < 2) { c->err = "max_frames must be >= 2"; return RB_ERR_INVALID; }
   if (rb_make_geom(cfg->width, cfg->height, cfg->grid_w, cfg->grid_h, cfg->overlap, cfg->weight_switch,
@@ -273,8 +313,74 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     return RB_ERR_INVALID;
   }
   RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kpm_smem));
+  RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kpm_smem));
 
   const size_t N = cfg->max_frames;
+  // ---- pipelined matcher: packed frame store, lists, TMA tensor map -------------------------------
+  {
+    c->pitch4 = rb_align_up((g.W + 1) / 2, 16);
+    c->frame_stride4 = (uint64_t)c->pitch4 * g.H;
+    RbKpmFastParams& f = c->fast;
+    memset(&f, 0, sizeof(f));
+    f.g = g;
+    uint32_t bx = 0, by = 0;
+    for (uint32_t s = 0; s < g.grid_w; ++s) {
+      const uint32_t tx0 = (g.col0[s] - 2) & ~31u, bytes = (g.col1[s] + 2 - tx0 + 1) / 2;
+      if (rb_align_up(bytes, 16) > bx) bx = rb_align_up(bytes, 16);
+    }
+    for (uint32_t s = 0; s < g.grid_h; ++s)
+      if (g.row1[s] - g.row0[s] + 4 > by) by = g.row1[s] - g.row0[s] + 4;
+    f.box_x = bx;
+    f.nbox_y = (by + 255) / 256;
+    f.box_y = (by + f.nbox_y - 1) / f.nbox_y;
+    uint32_t dxbits = 0, dybits = 0;
+    while ((1u << dxbits) <= 2 * g.W) ++dxbits;  // dx + W < 2 W, never all ones
+    while ((1u << dybits) <= 2 * g.H) ++dybits;
+    f.dybits = dybits;
+    f.offbits = dxbits + dybits;
+    const uint32_t cntmax = f.offbits < 32 ? (1u << (32 - f.offbits)) - 1u : 0u;
+    uint32_t cap = cfg->list_cap ? cfg->list_cap : 1024;
+    if (cap > 2047) cap = 2047;
+    if (cap > cntmax) cap = cntmax;  // a bin's count never exceeds the shorter list
+    cap &= ~3u;                      // 16-byte list rows
+    f.cap = cap;
+    f.tslots = next_pow2(2 * cap < 64 ? 64 : 2 * cap);
+    f.oslots = 1024;
+    f.run = cfg->run_pairs ? cfg->run_pairs : 32;
+    int smem_max = 0;
+    RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    c->fast_smem = rbf::smem_bytes(f);
+    const bool fast_ok = cap >= 16 && bx <= 256 && f.box_y <= 256 && c->fast_smem <= (size_t)smem_max && g.W < 16384;
+    if (!fast_ok && cfg->kpm_mode == 0) c->cfg.kpm_mode = 1;  // geometry outside the pipelined matcher's limits
+    if (c->cfg.kpm_mode == 0) {
+      RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fast_smem));
+      int occ = 0;
+      RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_kpm_fast_kernel, RB_FAST_NT, c->fast_smem));
+      c->fast_ctas_per_sm = occ < 1 ? 1 : occ;
+      RB_CUDA(c, dmalloc(c, &c->d_frames4, c->frame_stride4 * N + 256));
+      RB_CUDA(c, dmalloc(c, &c->d_lists, (size_t)N * g.nreg * cap * 4 + 256));
+      RB_CUDA(c, dmalloc(c, &c->d_counts, (size_t)N * g.nreg * sizeof(uint2)));
+      RB_CUDA(c, dmalloc(c, &c->d_deferred, (size_t)N * g.nreg * sizeof(uint2)));
+      RB_CUDA(c, dmalloc(c, &c->d_work, 256));
+      RB_CUDA(c, cudaMemsetAsync(c->d_frames4, 0, c->frame_stride4 * N + 256, c->stream));
+      RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 256, c->stream));
+      typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      RB_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      if (!fn || qres != cudaDriverEntryPointSuccess) { c->err = "cuTensorMapEncodeTiled unavailable"; return RB_ERR_CUDA; }
+      const cuuint64_t dims[3] = {c->pitch4, g.H, N};
+      const cuuint64_t strides[2] = {c->pitch4, c->frame_stride4};
+      const cuuint32_t box[3] = {f.box_x, f.box_y, 1};
+      const cuuint32_t estr[3] = {1, 1, 1};
+      const CUresult r = reinterpret_cast<encode_fn>(fn)(&c->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, c->d_frames4, dims, strides,
+                                                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { c->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return RB_ERR_CUDA; }
+    }
+  }
   RB_CUDA(c, dmalloc(c, &c->d_frames, g.frame_stride * N + 256));
   RB_CUDA(c, dmalloc(c, &c->d_kp, (size_t)N * g.H * g.NS * 4));
   RB_CUDA(c, dmalloc(c, &c->d_w2, (size_t)N * g.H * g.NS * 4));
@@ -302,6 +408,7 @@ void rb_destroy(rb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_frames4); cudaFree(c->d_lists); cudaFree(c->d_counts); cudaFree(c->d_deferred); cudaFree(c->d_work);
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
@@ -322,8 +429,7 @@ int rb_count_keypoints(rb_ctx* c, size_t first, size_t n, uint64_t* total) {
   RB_CUDA(c, cudaMemsetAsync(d, 0, 8, c->stream));
   const size_t nwords = n * c->g.H * c->g.NS;
   rb_count_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_kp + first * c->g.H * c->g.NS, nwords, d);
-  ++c->launches;
-  RB_CUDA(c, cudaGetLastError());
+  RB_LAUNCHED(c, "rb_count_kernel");
   unsigned long long h = 0;
   RB_CUDA(c, cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -333,6 +439,19 @@ int rb_count_keypoints(rb_ctx* c, size_t first, size_t n, uint64_t* total) {
 void* rb_stream(rb_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
 uint64_t rb_kernel_launches(rb_ctx* c) { return c ? c->launches : 0; }
 size_t rb_device_bytes(rb_ctx* c) { return c ? c->bytes : 0; }
+
+int rb_deferred_count(rb_ctx* c, uint32_t* count) {
+  if (!c || !count) return RB_ERR_INVALID;
+  *count = 0;
+  if (!c->d_work) return RB_OK;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  uint32_t w[4] = {0, 0, 0, 0};
+  RB_CUDA(c, cudaMemcpyAsync(w, c->d_work, 16, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  *count = w[1];
+  if (w[2]) { c->err = "pipelined matcher: a TMA transaction timed out"; return RB_ERR_CUDA; }
+  return RB_OK;
+}
 
 void* rb_alloc_host(size_t bytes) {
   void* p = nullptr;
@@ -361,6 +480,15 @@ int rb_upload(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
     RB_CUDA(c, cudaMemcpyAsync(dst, frames, (size_t)g.W * g.H * n, cudaMemcpyHostToDevice, c->stream));
   else
     RB_CUDA(c, cudaMemcpy2DAsync(dst, g.pitch, frames, g.W, g.W, (size_t)g.H * n, cudaMemcpyHostToDevice, c->stream));
+  if (c->d_frames4) {  // K0: the packed copy the pipelined matcher reads
+    const uint64_t chunks = (uint64_t)n * g.H * (g.pitch / 16);
+    uint64_t blocks = (chunks + 255) / 256;
+    const uint64_t maxb = (uint64_t)c->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    rb_pack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(dst, g.pitch, g.frame_stride, c->d_frames4 + c->frame_stride4 * first,
+                                                           c->pitch4, c->frame_stride4, g.H, (uint32_t)n);
+    RB_LAUNCHED(c, "rb_pack_kernel");
+  }
   if (first + n > c->uploaded) c->uploaded = first + n;
   return RB_OK;
 }
@@ -403,8 +531,7 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
     const size_t items = n * p.nseg * g.NS;
     const uint32_t blocks = (uint32_t)((items + 127) / 128);
     rb_kpe_kernel<<<blocks, 128, 0, c->stream>>>(p);
-    ++c->launches;
-    RB_CUDA(c, cudaGetLastError());
+    RB_LAUNCHED(c, "rb_kpe_kernel");
   }
   if (prof) RB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
   if (n >= 2) {
@@ -418,14 +545,42 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
     p.first_frame = (uint32_t)first;
     p.npairs = (uint32_t)(n - 1);
     p.code_slots = c->code_slots; p.off_slots = c->off_slots; p.tile_pitch = c->tile_pitch; p.tile_rows = c->tile_rows;
-    rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
-    ++c->launches;
-    RB_CUDA(c, cudaGetLastError());
+    if (c->cfg.kpm_mode == 0) {
+      // K1c: per-(frame, region) keypoint lists; K2: pipelined matcher; then the general kernel over
+      // whatever K2 deferred (normally nothing: the grid exits on an empty list)
+      const uint32_t items = (uint32_t)n * g.nreg;
+      uint32_t lblocks = (items + 7) / 8;
+      rb_list_kernel<<<lblocks, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)first, (uint32_t)n, c->fast.cap, c->d_lists,
+                                                    c->d_counts);
+      RB_LAUNCHED(c, "rb_list_kernel");
+      RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));  // work counter, deferred count, error word
+      RbKpmFastParams f = c->fast;
+      f.lists = c->d_lists;
+      f.counts = c->d_counts;
+      f.votes = c->d_votes;
+      f.first_frame = (uint32_t)first;
+      f.npairs = (uint32_t)(n - 1);
+      f.work_counter = c->d_work;
+      f.deferred_count = c->d_work + 1;
+      f.deferred = c->d_deferred;
+      f.deferred_cap = (uint32_t)((n - 1) * g.nreg);
+      const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
+      uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
+      if (grid > witems) grid = witems;
+      rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
+      RB_LAUNCHED(c, "rb_kpm_fast_kernel");
+      uint32_t dgrid = (uint32_t)c->sm_count * 2;
+      if (dgrid > f.deferred_cap) dgrid = f.deferred_cap;
+      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, c->d_deferred, c->d_work + 1, f.deferred_cap);
+      RB_LAUNCHED(c, "rb_kpm_deferred_kernel");
+    } else {
+      rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
+      RB_LAUNCHED(c, "rb_kpm_kernel");
+    }
     if (prof) RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, c->d_votes, c->d_results,
                                                                                    c->d_offsets, (uint32_t)(n - 1));
-    ++c->launches;
-    RB_CUDA(c, cudaGetLastError());
+    RB_LAUNCHED(c, "rb_declare_offsets_kernel");
   } else if (prof) {
     RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
   }
@@ -488,8 +643,7 @@ int rb_keypoints(rb_ctx* c, size_t frame, rb_keypoint* out, size_t cap, size_t* 
   rb_keypoints_kernel<<<1, 1024, (g.W + 1) * sizeof(uint32_t), c->stream>>>(
       g, c->d_frames + g.frame_stride * frame, c->d_kp + frame * g.H * g.NS, c->d_w2 + frame * g.H * g.NS, c->d_kps,
       dcap, c->d_tap_count);
-  ++c->launches;
-  RB_CUDA(c, cudaGetLastError());
+  RB_LAUNCHED(c, "rb_keypoints_kernel");
   uint32_t n = 0;
   RB_CUDA(c, cudaMemcpyAsync(&n, c->d_tap_count, 4, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -531,8 +685,7 @@ int rb_region_votes(rb_ctx* c, size_t pair, uint32_t region, rb_bin* out, size_t
   p.tap_pair = 0; p.tap_region = region;
   // launch all regions of the pair (blockIdx -> region), only `region` dumps
   rb_kpm_kernel<<<g.nreg, 256, c->kpm_smem, c->stream>>>(p);
-  ++c->launches;
-  RB_CUDA(c, cudaGetLastError());
+  RB_LAUNCHED(c, "rb_kpm_kernel");
   uint32_t n = 0;
   RB_CUDA(c, cudaMemcpyAsync(&n, c->d_tap_count, 4, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -565,8 +718,7 @@ static int fgmask_common(rb_ctx* c, const uint8_t* bg, uint32_t bgW, uint32_t bg
   const uint32_t cap = (uint32_t)c->sm_count * 8;
   if (blocks > cap) blocks = cap;
   rb_fgmask_kernel<<<blocks, 256, 0, c->stream>>>(c->d_bg, idx, bgW, dframe, fpitch, c->d_mask, g.W, g.W, g.H);
-  ++c->launches;
-  RB_CUDA(c, cudaGetLastError());
+  RB_LAUNCHED(c, "rb_fgmask_kernel");
   if (out_mask)
     RB_CUDA(c, cudaMemcpyAsync(out_mask, c->d_mask, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));

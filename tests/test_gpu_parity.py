@@ -63,11 +63,53 @@ ORACLE_CASES = {
 }
 
 
+# matcher variants: the pipelined matcher (default), the general kernel alone, the pipelined matcher with
+# a list capacity so small that most regions are deferred to the general kernel, and short runs
+MATCHER_MODES = {
+    "pipelined": {},
+    "general": dict(kpm_mode=1),
+    "tiny_cap": dict(list_cap=64),
+    "run3": dict(run_pairs=3),
+}
+
+
+@pytest.mark.parametrize("mode", sorted(MATCHER_MODES))
 @pytest.mark.parametrize("name", sorted(ORACLE_CASES))
-def test_cuda_matches_oracle(name):
+def test_cuda_matches_oracle(name, mode):
     make, kw = ORACLE_CASES[name]
     frames = make()
-    gpu_common.compare_with_oracle(frames, oracle, name, taps=((0, 0), (0, 3), (0, 7), (frames.shape[0] - 2, 5)), **kw)
+    kw = dict(kw, **MATCHER_MODES[mode])
+    gpu_common.compare_with_oracle(frames, oracle, f"{name}/{mode}", taps=((0, 0), (0, 3), (0, 7), (frames.shape[0] - 2, 5)),
+                                   **kw)
+
+
+def test_pipelined_matcher_equals_general_kernel_ballot_for_ballot():
+    """Same frames through both matchers: every field of every region ballot of every pair."""
+    n = 200
+    seq = synth.scrolling_tilemap(n, 320, 224, seed=77, cut_every=40, sprites=6)
+    outs = []
+    for kw in (dict(), dict(kpm_mode=1), dict(list_cap=256, run_pairs=7)):
+        with remap_b200.Registrar(320, 224, max_frames=n, **kw) as reg:
+            reg.upload(seq.frames)
+            off, _ = reg.register(n)
+            ballots = np.stack([reg.region_ballots(i) for i in range(n - 1)])
+            outs.append((off.copy(), ballots, reg.deferred_count))
+    # scene cuts make thousands of spurious offsets in a region: those few pairs overflow the offset table
+    assert outs[0][2] < 40, "the pipelined matcher should defer next to nothing on a scrolling workload"
+    assert outs[2][2] > 0, "list_cap=256 should exercise the deferral path"
+    for off, ballots, _ in outs[1:]:
+        assert np.array_equal(off, outs[0][0])
+        for fld in ballots.dtype.names:
+            assert np.array_equal(ballots[fld], outs[0][1][fld]), fld
+
+
+def test_pipelined_matcher_defers_nothing_on_config2_frames():
+    n = 500
+    seq = synth.scrolling_tilemap(n, 320, 224, seed=1)
+    with remap_b200.Registrar(320, 224, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        reg.register(n)
+        assert reg.deferred_count == 0
 
 
 def test_dirty_high_nibbles_are_ignored():
