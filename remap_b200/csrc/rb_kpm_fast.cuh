@@ -34,10 +34,11 @@
 
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
-#ifndef RB_FAST_NT
-#define RB_FAST_NT 512
+#ifndef RB_FAST_NWP
+#define RB_FAST_NWP 23  // warps that build / probe / vote (768 threads with the ballot warp: 40 registers at 2 CTAs per SM)
 #endif
-#define RB_MAX_OSLOTS_PER_THREAD 8  // offset table <= 2048 slots
+#define RB_FAST_NTP (32 * RB_FAST_NWP)
+#define RB_FAST_NT (RB_FAST_NTP + 32)  // + one warp that turns finished offset tables into ballots
 
 struct RbKpmFastParams {
   RbGeom g;
@@ -45,14 +46,14 @@ struct RbKpmFastParams {
   const uint2* counts;     // [frame][region] (n_all, n_w2)
   RbRegionVote* votes;     // [npairs][nreg]
   uint32_t first_frame, npairs;
-  uint32_t cap;            // list capacity (<= 2048)
+  uint32_t cap;            // list capacity (<= 2047)
   uint32_t tslots;         // code table slots, power of two >= 2 * cap
-  uint32_t oslots;         // offset table slots, power of two, multiple of RB_FAST_NT
+  uint32_t oslots;         // offset table slots, power of two
   uint32_t run;            // pairs per work item
   uint32_t box_x, box_y;   // TMA box: bytes per tile row, rows per box
   uint32_t nbox_y;         // boxes stacked vertically per tile (tile rows = nbox_y * box_y)
   uint32_t dybits, offbits;  // offset id = (dx + W) << dybits | (dy + H), offbits bits in all
-  uint32_t* work_counter;  // zeroed before launch
+  uint32_t* work_counter;  // [0] work items, [2] error word; zeroed before launch
   uint32_t* deferred_count;
   uint2* deferred;         // (pair, region)
   uint32_t deferred_cap;
@@ -61,6 +62,7 @@ struct RbKpmFastParams {
 namespace rbf {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t NONE = 0x80000000u;  // "no offset": never a valid offset id (offbits <= 24)
 constexpr uint32_t MAXPROBE = 96;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -88,6 +90,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
     if (spin > (1u << 22)) { *error_word = 1u; break; }
 }
+// NOTE (measured on B200): the innermost TMA coordinate times the element size must be a multiple
+// of 16 bytes; an unaligned start raises "illegal instruction".  Tiles therefore start at 32-pixel
+// boundaries of the 4 bit/pixel store.
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint32_t x, uint32_t y, uint32_t z, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
@@ -101,18 +106,23 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                : "memory");
 }
 
-struct Smem {           // two stages of everything per-frame: stage k lives at base + k * stride
+struct Smem {           // stage k of a per-frame array lives at base + k * stride
   uint8_t* tile;        // [2][tile_rows][box_x] packed 4 bit/pixel, + 16 bytes of slack
   uint32_t* plist;      // [2][cap] positions as delivered by the bulk copy
-  uint4* ents;          // [2][cap] (c0, c1, c2, pos): the frame's codes, kept for its turn as "previous"
-  uint32_t* ctab;       // [2][tslots] idx | c3 << 11 | 16 hash bits << 15 (bit 31 clear), or EMPTY
-  uint32_t tile_stride, plist_stride;  // bytes / words between the stages
-  uint32_t* otab;       // [oslots] offset id << cntbits | count, or EMPTY
-  uint32_t* cand;       // [NW * 3 + NW] per-warp ticket candidates and bin counts (NW <= 16)
-  uint32_t* stat;       // [2][4]: bins tied with ticket 0/1/2, overflow flag
-  uint32_t* misc;       // [4]: work item
+  uint4* ents;          // [2][cap] (c0, c1, c2, pos | c3 << 28): the frame's codes, kept for its turn as "previous"
+  uint16_t* next;       // [2][cap] chain links: next entry of the same frame in the same bucket, or NIL16
+  uint32_t* head;       // [3][tslots] first entry of each bucket's chain, or NIL
+  uint32_t* otab;       // [2][oslots] offset id << cntbits | count, or EMPTY
+  uint16_t* touched;    // [2][oslots] slots claimed in otab
+  uint32_t* plan;       // [run + 3] per-step control words of the current work item (see PLAN_*)
+  uint32_t* ctl;        // [0..1] touched counts, [2..3] overflow flags, [4] work item
   uint64_t* mbar;       // [2]
+  uint32_t tile_stride, plist_stride;  // bytes / words between the stages
 };
+
+// plan word of step t (frame fa + t): entries taking part | flags | n_all of the frame
+constexpr uint32_t PLAN_LMASK = 0x7FFu, PLAN_FITS = 1u << 11, PLAN_PAIR_OK = 1u << 12, PLAN_USE_ALL = 1u << 13;
+constexpr uint32_t PLAN_NALL_SHIFT = 16;
 
 __host__ __device__ inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -125,10 +135,13 @@ __host__ __device__ inline size_t smem_bytes(const RbKpmFastParams& p) {
   b += 2 * tile_bytes(p);
   b += 2 * align_up_sz((size_t)p.cap * 4, 128);
   b += 2 * (size_t)p.cap * 16;
-  b += 2 * (size_t)p.tslots * 4;
-  b += (size_t)p.oslots * 4;
-  b += 64 * 4 + 8 * 4 + 4 * 4 + 2 * 8;
-  return b + 128;  // base alignment slack
+  b += align_up_sz(2 * (size_t)p.cap * 2, 16);
+  b += 3 * (size_t)p.tslots * 4;
+  b += 2 * (size_t)p.oslots * 4;
+  b += 2 * (size_t)p.oslots * 2;
+  b += align_up_sz(((size_t)p.run + 3) * 4, 16);
+  b += 8 * 4 + 2 * 8;
+  return b;
 }
 
 // Pointers are formed as (shared array + offset) so that the compiler keeps them in the shared
@@ -141,11 +154,12 @@ __device__ __forceinline__ void carve(const RbKpmFastParams& p, uint8_t* base, S
   s.tile = base + o; o += 2 * tile_bytes(p);
   s.plist = reinterpret_cast<uint32_t*>(base + o); o += 2 * align_up_sz((size_t)p.cap * 4, 128);
   s.ents = reinterpret_cast<uint4*>(base + o); o += 2 * (size_t)p.cap * 16;
-  s.ctab = reinterpret_cast<uint32_t*>(base + o); o += 2 * (size_t)p.tslots * 4;
-  s.otab = reinterpret_cast<uint32_t*>(base + o); o += (size_t)p.oslots * 4;
-  s.cand = reinterpret_cast<uint32_t*>(base + o); o += 64 * 4;
-  s.stat = reinterpret_cast<uint32_t*>(base + o); o += 8 * 4;
-  s.misc = reinterpret_cast<uint32_t*>(base + o); o += 4 * 4;
+  s.next = reinterpret_cast<uint16_t*>(base + o); o += align_up_sz(2 * (size_t)p.cap * 2, 16);
+  s.head = reinterpret_cast<uint32_t*>(base + o); o += 3 * (size_t)p.tslots * 4;
+  s.otab = reinterpret_cast<uint32_t*>(base + o); o += 2 * (size_t)p.oslots * 4;
+  s.touched = reinterpret_cast<uint16_t*>(base + o); o += 2 * (size_t)p.oslots * 2;
+  s.plan = reinterpret_cast<uint32_t*>(base + o); o += align_up_sz(((size_t)p.run + 3) * 4, 16);
+  s.ctl = reinterpret_cast<uint32_t*>(base + o); o += 8 * 4;
   s.mbar = reinterpret_cast<uint64_t*>(base + o);
 }
 
@@ -198,21 +212,19 @@ __device__ __forceinline__ void warp_top3(uint32_t t0, uint32_t t1, uint32_t t2,
   m2 = __reduce_max_sync(0xffffffffu, t0);
 }
 
+constexpr uint32_t NIL = 0xFFFFFFFFu;
+
 }  // namespace rbf
 
-__global__ void __launch_bounds__(RB_FAST_NT) rb_kpm_fast_kernel(const __grid_constant__ CUtensorMap tmap, const RbKpmFastParams p) {
+__global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid_constant__ CUtensorMap tmap, const RbKpmFastParams p) {
   using namespace rbf;
   extern __shared__ __align__(128) uint8_t rb_fast_smem[];
   Smem s;
   carve(p, rb_fast_smem, s);
   const RbGeom& g = p.g;
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr uint32_t NT = RB_FAST_NT, NW = RB_FAST_NT / 32;
-  const uint32_t tmask = p.tslots - 1, omask = p.oslots - 1;
-  const uint32_t cntbits = 32 - p.offbits, cntmask = (1u << cntbits) - 1u, offmask = (1u << p.offbits) - 1u;
-  const uint32_t wpr = p.box_x / 4;
-  const uint32_t tile_tx_bytes = p.box_x * p.box_y * p.nbox_y;
-  const uint32_t rv = g.region_votes;
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  constexpr uint32_t NT = RB_FAST_NT, NTP = RB_FAST_NTP;
+  const bool ballot_warp = tid >= NTP;
   const uint32_t runs = (p.npairs + p.run - 1) / p.run;
   const uint32_t nitems = runs * g.nreg;
 
@@ -223,230 +235,233 @@ __global__ void __launch_bounds__(RB_FAST_NT) rb_kpm_fast_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (uint32_t i = tid; i < 2 * p.tslots; i += NT) s.ctab[i] = EMPTY;
-  for (uint32_t i = tid; i < p.oslots; i += NT) s.otab[i] = EMPTY;
-  if (tid < 8) s.stat[tid] = 0;
+  for (uint32_t i = tid; i < 3 * p.tslots; i += NT) s.head[i] = NIL;
+  for (uint32_t i = tid; i < 2 * p.oslots; i += NT) s.otab[i] = EMPTY;
+  if (tid < 8) s.ctl[tid] = 0;
   __syncthreads();
   uint32_t ph0 = 0, ph1 = 0;  // mbarrier phase parities (persist across work items)
-  uint32_t spar = 0;          // stat[] double buffer
+
+  // ---- the ballot warp's job: one finished offset table -> one RbRegionVote ----------------------
+  // t = step whose votes are in the table (pair = frames fa + t - 1, fa + t)
+  auto make_ballot = [&](uint32_t t, uint32_t fa, uint32_t region) {
+    const uint32_t par = t & 1, w = s.plan[t];
+    const uint32_t cntbits = 32 - p.offbits, cntmask = (1u << cntbits) - 1u, offmask = (1u << p.offbits) - 1u;
+    uint32_t* otab = s.otab + par * p.oslots;
+    const uint16_t* touched = s.touched + par * p.oslots;
+    const uint32_t nt = s.ctl[par];
+    const bool overflow = s.ctl[2 + par] != 0;
+    const uint32_t pairidx = fa + t - 1 - p.first_frame;
+    if ((w & PLAN_PAIR_OK) && !overflow) {
+      uint32_t t0 = 0, t1 = 0, t2 = 0;
+      for (uint32_t j = lane; j < nt; j += 32) {
+        const uint32_t v = otab[touched[j]];
+        // larger key = earlier in the ticket: count desc, then offset id asc (dx asc, dy asc)
+        top3_insert(((v & cntmask) << p.offbits) | (offmask - (v >> cntbits)), t0, t1, t2);
+      }
+      uint32_t g0, g1, g2;
+      warp_top3(t0, t1, t2, g0, g1, g2);
+      const uint32_t c0 = g0 >> p.offbits, c1 = g1 >> p.offbits, c2 = g2 >> p.offbits;
+      uint32_t e01 = 0, e2 = 0;  // bins tied with ticket 0 / 1 (16 bits each) and 2
+      for (uint32_t j = lane; j < nt; j += 32) {
+        const uint32_t sl = touched[j];
+        const uint32_t c = otab[sl] & cntmask;
+        e01 += (c == c0 ? 1u : 0u) + (c == c1 ? 0x10000u : 0u);
+        e2 += c == c2;
+        otab[sl] = EMPTY;
+      }
+      e01 = __reduce_add_sync(0xffffffffu, e01);
+      e2 = __reduce_add_sync(0xffffffffu, e2);
+      if (lane == 0) {
+        const uint32_t rv = g.region_votes;
+        const uint2 cp = __ldg(p.counts + (uint64_t)(fa + t - 1) * g.nreg + region);
+        const uint2 cc = __ldg(p.counts + (uint64_t)(fa + t) * g.nreg + region);
+        const uint32_t E0 = e01 & 0xFFFFu, E1 = e01 >> 16, E2 = e2;
+        RbRegionVote vt;
+        vt.use_all = (w & PLAN_USE_ALL) ? 1u : 0u;
+        vt.n_prev = cp.x; vt.n_curr = cc.x; vt.w2_prev = cp.y; vt.w2_curr = cc.y;
+        vt.nbins = nt;
+        vt.nticket = nt < rv ? nt : rv;
+        const uint32_t gk[3] = {g0, g1, g2}, ck[3] = {c0, c1, c2};
+        // bins with a larger / larger-or-equal count than ticket k (counts are sorted c0 >= c1 >= c2)
+        uint32_t ngt[3], nge[3];
+        ngt[0] = 0; nge[0] = E0;
+        ngt[1] = c1 == c0 ? 0u : nge[0]; nge[1] = ngt[1] + E1;
+        ngt[2] = c2 == c1 ? ngt[1] : nge[1]; nge[2] = ngt[2] + E2;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          RbBin b; b.dx = 0; b.dy = 0; b.cnt = 0;
+          vt.ticket[k] = b; vt.ngt[k] = 0; vt.nge[k] = 0;
+          if (k < 3 && k < vt.nticket) {
+            const uint32_t oid = offmask - (gk[k] & offmask);
+            vt.ticket[k].dx = (int32_t)(oid >> p.dybits) - (int32_t)g.W;
+            vt.ticket[k].dy = (int32_t)(oid & ((1u << p.dybits) - 1u)) - (int32_t)g.H;
+            vt.ticket[k].cnt = ck[k];
+            vt.ngt[k] = ngt[k]; vt.nge[k] = nge[k];
+          }
+        }
+        p.votes[(uint64_t)pairidx * g.nreg + region] = vt;
+      }
+    } else {
+      // the pair cannot be finished here (a list or the offset table does not fit): defer it
+      if (lane == 0) {
+        const uint32_t at = atomicAdd(p.deferred_count, 1u);
+        if (at < p.deferred_cap) p.deferred[at] = make_uint2(pairidx, region);
+      }
+      if (overflow) { for (uint32_t i = lane; i < p.oslots; i += 32) otab[i] = EMPTY; }
+      else { for (uint32_t j = lane; j < nt; j += 32) otab[touched[j]] = EMPTY; }
+    }
+    __syncwarp();
+    if (lane == 0) { s.ctl[par] = 0; s.ctl[2 + par] = 0; }
+  };
 
   for (;;) {
-    if (tid == 0) s.misc[0] = atomicAdd(p.work_counter, 1u);
+    if (tid == 0) s.ctl[4] = atomicAdd(p.work_counter, 1u);
     __syncthreads();
-    const uint32_t item = s.misc[0];
+    const uint32_t item = s.ctl[4];
     if (item >= nitems) break;
     // regions vary fastest so that the CTAs running at the same time share frames in L2
     const uint32_t region = item % g.nreg, runidx = item / g.nreg;
     const uint32_t pa = runidx * p.run;
     const uint32_t pb = pa + p.run < p.npairs ? pa + p.run : p.npairs;  // pairs [pa, pb)
-    const uint32_t fa = p.first_frame + pa, fb = p.first_frame + pb;   // frames fa .. fb inclusive
+    const uint32_t fa = p.first_frame + pa;                             // frames fa .. fa + nsteps - 1
+    const uint32_t nsteps = pb - pa + 1;
     const uint32_t cs = region / g.grid_h, rs = region % g.grid_h;     // idx = grid_h*col + row (src/kpr.hpp:71-74)
     const uint32_t X0 = g.col0[cs], Y0 = g.row0[rs];
-    const uint32_t tx0 = (X0 - 2) & ~31u;  // tile origin: TMA wants the inner coordinate 16-byte aligned (32 px)
-    const uint2* cnts = p.counts + region;
+    const uint32_t tx0 = (X0 - 2) & ~31u;  // tile origin (pixels), see tma_load_3d
 
-    auto request = [&](uint32_t frame, uint32_t stage, uint32_t n_all) {  // thread 0 only
-      const uint32_t n = n_all < p.cap ? n_all : p.cap;
-      const uint32_t lbytes = (n * 4 + 15) & ~15u;
-      mbar_expect_tx(&s.mbar[stage], tile_tx_bytes + lbytes);
+    // ---- the run's plan: one control word per step, computed once, by one thread per step ----------
+    if (tid < nsteps) {
+      const uint2* cnts = p.counts + (uint64_t)fa * g.nreg + region;
+      const uint32_t t = tid, ws = g.weight_switch;
+      auto load = [&](int k) { return k >= 0 && k < (int)nsteps ? __ldg(cnts + (uint64_t)k * g.nreg) : make_uint2(0, 0); };
+      const uint2 cm2 = load((int)t - 2), cm1 = load((int)t - 1), c0 = load((int)t), cp1 = load((int)t + 1);
+      // weight switch of a pair (a, b): src/kpm.hpp:219-220 ('<' on previous, '<=' on current)
+      auto sw = [&](const uint2& a, const uint2& b) { return a.y < ws || b.y <= ws; };
+      const bool ua_m1 = t >= 2 && sw(cm2, cm1);               // pair (t - 2, t - 1)
+      const bool ua_0 = t >= 1 && sw(cm1, c0);                 // pair (t - 1, t)
+      const bool ua_p1 = t + 1 < nsteps && sw(c0, cp1);        // pair (t, t + 1)
+      const uint32_t L = (ua_0 || ua_p1) ? c0.x : c0.y;        // entries of this frame that take part
+      const uint32_t Lm1 = (ua_m1 || ua_0) ? cm1.x : cm1.y;    // ... of the previous frame
+      const bool fits = L <= p.cap, fits_m1 = Lm1 <= p.cap;
+      uint32_t w = (fits ? (L | PLAN_FITS) : 0u) | (ua_0 ? PLAN_USE_ALL : 0u);
+      if (t >= 1 && fits && fits_m1) w |= PLAN_PAIR_OK;
+      const uint32_t nall = c0.x < p.cap ? c0.x : p.cap;
+      s.plan[t] = w | (nall << PLAN_NALL_SHIFT);
+    }
+    __syncthreads();
+
+    auto request = [&](uint32_t t) {  // thread 0 only: tile + list of step t into stage t & 1
+      const uint32_t stage = t & 1, frame = fa + t;
+      const uint32_t lbytes = ((s.plan[t] >> PLAN_NALL_SHIFT) * 4 + 15) & ~15u;
+      mbar_expect_tx(&s.mbar[stage], p.box_x * p.box_y * p.nbox_y + lbytes);
       for (uint32_t b = 0; b < p.nbox_y; ++b)
         tma_load_3d(s.tile + stage * s.tile_stride + b * p.box_x * p.box_y, &tmap, tx0 / 2, Y0 - 2 + b * p.box_y, frame,
                     &s.mbar[stage]);
       if (lbytes) bulk_load(s.plist + stage * s.plist_stride, p.lists + ((uint64_t)frame * g.nreg + region) * p.cap, lbytes, &s.mbar[stage]);
     };
-
-    // counts of frames f, f + 1, f + 2 (rolling registers, block-uniform)
-    uint2 cA = __ldg(cnts + (uint64_t)fa * g.nreg);
-    uint2 cB = fa + 1 <= fb ? __ldg(cnts + (uint64_t)(fa + 1) * g.nreg) : make_uint2(0, 0);
-    uint2 cC = make_uint2(0, 0);
     if (tid == 0) {
-      request(fa, 0, cA.x);
-      if (fa + 1 <= fb) request(fa + 1, 1, cB.x);
+      request(0);
+      if (nsteps > 1) request(1);
     }
-    bool prev_valid = false;
-    uint32_t prev_n = 0, prev_w2 = 0;
-    bool use_all = false;  // weight switch of the pair (f - 1, f)
+    uint32_t tb = 0;  // bucket table built in this step; probed table = tb - 1, table to clear = tb + 1 (mod 3)
 
-    for (uint32_t f = fa, t = 0; f <= fb; ++f, ++t) {
+    for (uint32_t t = 0; t < nsteps; ++t) {
       const uint32_t st = t & 1;
-      if (f + 2 <= fb) cC = __ldg(cnts + (uint64_t)(f + 2) * g.nreg);
-      // src/kpm.hpp:219-220 ('<' on previous, '<=' on current), for the pair (f, f + 1)
-      const bool use_all_next = f < fb && ((cA.y < g.weight_switch) || (cB.y <= g.weight_switch));
-      const bool need_w1 = (t > 0 && use_all) || use_all_next;
-      const uint32_t L = need_w1 ? cA.x : cA.y;  // entries of this frame that take part
-      const bool fits = L <= p.cap;
-      const bool pair = t > 0;
-      const bool pair_ok = pair && prev_valid && fits;
+      if (!ballot_warp) {
+        const uint32_t w = s.plan[t];
+        const uint32_t tp = tb >= 1 ? tb - 1 : 2, tc = tb == 2 ? 0 : tb + 1;
+        // the table that will be built next step still holds the chains of two steps ago
+        {
+          uint4* hc = reinterpret_cast<uint4*>(s.head + tc * p.tslots);
+          for (uint32_t i = tid; i < p.tslots / 4; i += NTP) hc[i] = make_uint4(NIL, NIL, NIL, NIL);
+        }
+        if (st == 0) { mbar_wait(&s.mbar[0], ph0, p.work_counter + 2); ph0 ^= 1; }
+        else { mbar_wait(&s.mbar[1], ph1, p.work_counter + 2); ph1 ^= 1; }
 
-      if (st == 0) { mbar_wait(&s.mbar[0], ph0, p.work_counter + 2); ph0 ^= 1; }
-      else { mbar_wait(&s.mbar[1], ph1, p.work_counter + 2); ph1 ^= 1; }
-
-      // ---- P: codes, build this frame's table, probe the previous one, vote --------------------
-      if (fits) {
-        const uint32_t* tile = reinterpret_cast<const uint32_t*>(s.tile + st * s.tile_stride);
-        const uint32_t* plist = s.plist + st * s.plist_stride;
-        uint4* ents = s.ents + st * p.cap;
-        const uint4* pents = s.ents + (st ^ 1) * p.cap;
-        uint32_t* ctab = s.ctab + st * p.tslots;
-        const uint32_t* ptab = s.ctab + (st ^ 1) * p.tslots;
-        // One bin usually takes nearly every vote of a region (the true camera offset), so votes are
-        // aggregated per warp first: lanes with the same offset elect a leader that adds their number.
-        auto vote = [&](uint32_t oid, uint32_t k) {
-          uint32_t os = off_hash(oid) & omask;
-          uint32_t probes = 0;
-          for (;;) {
-            uint32_t v = s.otab[os];
-            if (v == EMPTY) {
-              v = atomicCAS(&s.otab[os], EMPTY, (oid << cntbits) | k);
-              if (v == EMPTY) break;
+        // ---- codes, build this frame's buckets, probe the previous frame's, vote -------------------
+        if (w & PLAN_FITS) {
+          const uint32_t L = w & PLAN_LMASK;
+          const bool pair_ok = (w & PLAN_PAIR_OK) != 0, use_all = (w & PLAN_USE_ALL) != 0;
+          const uint32_t tmask = p.tslots - 1, omask = p.oslots - 1, cntbits = 32 - p.offbits, wpr = p.box_x / 4;
+          const uint32_t* tile = reinterpret_cast<const uint32_t*>(s.tile + st * s.tile_stride);
+          const uint32_t* plist = s.plist + st * s.plist_stride;
+          uint4* ents = s.ents + st * p.cap;
+          uint16_t* next = s.next + st * p.cap;
+          const uint4* pents = s.ents + (st ^ 1) * p.cap;
+          const uint16_t* pnext = s.next + (st ^ 1) * p.cap;
+          uint32_t* head = s.head + tb * p.tslots;
+          const uint32_t* phead = s.head + tp * p.tslots;
+          uint32_t* otab = s.otab + st * p.oslots;
+          uint16_t* touched = s.touched + st * p.oslots;
+          // One bin usually takes nearly every vote of a region (the true camera offset), so votes are
+          // aggregated per warp first: lanes with the same offset elect a leader that adds their number.
+          auto vote = [&](uint32_t oid, uint32_t k) {
+            uint32_t os = off_hash(oid) & omask;
+            uint32_t probes = 0;
+            for (;;) {
+              uint32_t v = otab[os];
+              if (v == EMPTY) {
+                v = atomicCAS(&otab[os], EMPTY, (oid << cntbits) | k);
+                if (v == EMPTY) { touched[atomicAdd(&s.ctl[st], 1u)] = (uint16_t)os; break; }
+              }
+              if ((v >> cntbits) == oid) { atomicAdd(&otab[os], k); break; }
+              os = (os + 1) & omask;
+              if (++probes > MAXPROBE) { s.ctl[2 + st] = 1; break; }  // table (nearly) full: defer
             }
-            if ((v >> cntbits) == oid) { atomicAdd(&s.otab[os], k); break; }
-            os = (os + 1) & omask;
-            if (++probes > MAXPROBE) { s.stat[spar * 4 + 3] = 1; break; }  // table (nearly) full: defer
-          }
-        };
-        const uint32_t Lw = (L + 31) & ~31u;  // whole warps iterate together
-        for (uint32_t i = tid; i < Lw; i += NT) {
-          uint32_t first_oid = 0x80000000u | lane;  // "no vote": unique per lane
-          if (i < L) {
-            const uint32_t pos = plist[i];
-            const uint32_t x = pos & 0x7FFFu, y = pos >> 16;
-            const Code c = code_at(tile, wpr, x - 2 - tx0, y - Y0);
-            const uint32_t h = code_hash(c);
-            ents[i] = make_uint4(c.c0, c.c1, c.c2, pos);
-            const uint32_t tag = (c.c3 << 11) | ((h >> 16) << 15);  // bit 31 stays clear: h >> 16 has 16 bits
-            {
-              uint32_t slot = h & tmask;
-              while (atomicCAS(&ctab[slot], EMPTY, tag | i) != EMPTY) slot = (slot + 1) & tmask;
-            }
-            if (pair_ok && (use_all || (pos & 0x8000u))) {  // !use_all: weight-2 codes only (src/kpm.hpp:113-117)
-              uint32_t slot = h & tmask, e;
-              while ((e = ptab[slot]) != EMPTY) {
-                if (((e ^ tag) >> 11) == 0) {
-                  const uint4 pe = pents[e & 0x7FFu];
-                  if (pe.x == c.c0 && pe.y == c.c1 && pe.z == c.c2) {
-                    // offset = prev - curr (src/kpm.hpp:96-98)
-                    const uint32_t dxb = (pe.w & 0x7FFFu) - x + g.W, dyb = (pe.w >> 16) - y + g.H;
-                    const uint32_t oid = (dxb << p.dybits) | dyb;
-                    if (first_oid & 0x80000000u) first_oid = oid; else vote(oid, 1u);
+          };
+          const uint32_t Lw = (L + 31) & ~31u;  // whole warps iterate together
+          for (uint32_t i = tid; i < Lw; i += NTP) {
+            uint32_t oid0 = NONE | lane, oid1 = NONE | lane;  // unique per lane: groups of one in match_any
+            if (i < L) {
+              const uint32_t pos = plist[i];
+              const uint32_t x = pos & 0x7FFFu, y = pos >> 16;
+              const Code c = code_at(tile, wpr, x - 2 - tx0, y - Y0);
+              const uint32_t slot = code_hash(c) & tmask;
+              const uint32_t w3 = pos | (c.c3 << 28);  // y < 4096: the top nibble is free for the code's last 4 bits
+              ents[i] = make_uint4(c.c0, c.c1, c.c2, w3);
+              next[i] = (uint16_t)atomicExch(&head[slot], i);  // push onto the bucket's chain (NIL -> 0xFFFF)
+              if (pair_ok && (use_all || (pos & 0x8000u))) {   // !use_all: weight-2 codes only (src/kpm.hpp:113-117)
+                uint32_t j = phead[slot];
+                while (j != NIL) {
+                  const uint4 pe = pents[j];
+                  if (pe.x == c.c0 && pe.y == c.c1 && pe.z == c.c2 && ((pe.w ^ w3) >> 28) == 0) {
+                    // equal codes: vote prev - curr (src/kpm.hpp:96-98)
+                    const uint32_t oid = ((((pe.w & 0x7FFFu) - x + g.W) << p.dybits) | (((pe.w >> 16) & 0xFFFu) - y + g.H));
+                    if (oid0 & NONE) oid0 = oid;
+                    else if (oid1 & NONE) oid1 = oid;
+                    else vote(oid, 1u);  // third and later matches of one keypoint: rare, one by one
                   }
+                  const uint32_t nx = pnext[j];
+                  j = nx == 0xFFFFu ? NIL : nx;
                 }
-                slot = (slot + 1) & tmask;
+              }
+            }
+            if (pair_ok) {
+              const uint32_t grp = __match_any_sync(0xffffffffu, oid0);
+              if (!(oid0 & NONE) && lane == (uint32_t)(__ffs((int)grp) - 1)) vote(oid0, (uint32_t)__popc(grp));
+              if (__any_sync(0xffffffffu, !(oid1 & NONE))) {
+                const uint32_t grp1 = __match_any_sync(0xffffffffu, oid1);
+                if (!(oid1 & NONE) && lane == (uint32_t)(__ffs((int)grp1) - 1)) vote(oid1, (uint32_t)__popc(grp1));
               }
             }
           }
-          const uint32_t grp = __match_any_sync(0xffffffffu, first_oid);
-          if (!(first_oid & 0x80000000u) && lane == (uint32_t)(__ffs((int)grp) - 1)) vote(first_oid, (uint32_t)__popc(grp));
         }
+        tb = tc;
+      } else if (t >= 2) {
+        make_ballot(t - 1, fa, region);  // the pair voted on during the previous step
       }
-      __syncthreads();  // B2: votes complete; tile[st] / plist[st] consumed
-
-      if (tid == 0 && f + 2 <= fb) request(f + 2, st, cC.x);
-
-      if (pair) {
-        const uint32_t pairidx = f - 1 - p.first_frame;
-        const bool overflow = s.stat[spar * 4 + 3] != 0;
-        if (pair_ok && !overflow) {
-          // ---- S: ticket, tie statistics ----------------------------------------------------
-          uint32_t v[RB_MAX_OSLOTS_PER_THREAD];
-          uint32_t t0 = 0, t1 = 0, t2 = 0, nb = 0;
-          const uint32_t per = p.oslots / NT;
-#pragma unroll
-          for (uint32_t k = 0; k < RB_MAX_OSLOTS_PER_THREAD; ++k) {
-            v[k] = EMPTY;
-            if (k < per) {
-              v[k] = s.otab[tid + k * NT];
-              if (v[k] != EMPTY) {
-                ++nb;
-                // larger key = earlier in the ticket: count desc, then offset id asc (dx asc, dy asc)
-                top3_insert(((v[k] & cntmask) << p.offbits) | (offmask - (v[k] >> cntbits)), t0, t1, t2);
-              }
-            }
-          }
-          uint32_t m0, m1, m2;
-          warp_top3(t0, t1, t2, m0, m1, m2);
-          nb = __reduce_add_sync(0xffffffffu, nb);
-          if (lane == 0) {
-            s.cand[warp * 3] = m0; s.cand[warp * 3 + 1] = m1; s.cand[warp * 3 + 2] = m2;
-            s.cand[NW * 3 + warp] = nb;
-          }
-          __syncthreads();  // B3
-          uint32_t cv0 = lane < NW * 3 ? s.cand[lane] : 0u, cv1 = 0, cv2 = 0;
-          if (lane + 32 < NW * 3) top3_insert(s.cand[lane + 32], cv0, cv1, cv2);
-          uint32_t g0, g1, g2;
-          warp_top3(cv0, cv1, cv2, g0, g1, g2);
-          const uint32_t nbins = __reduce_add_sync(0xffffffffu, lane < NW ? s.cand[NW * 3 + lane] : 0u);
-          const uint32_t c0 = g0 >> p.offbits, c1 = g1 >> p.offbits, c2 = g2 >> p.offbits;
-          uint32_t e0 = 0, e1 = 0, e2 = 0;
-#pragma unroll
-          for (uint32_t k = 0; k < RB_MAX_OSLOTS_PER_THREAD; ++k) {
-            if (k < per && v[k] != EMPTY) {
-              const uint32_t c = v[k] & cntmask;
-              e0 += c == c0; e1 += c == c1; e2 += c == c2;
-              s.otab[tid + k * NT] = EMPTY;
-            }
-          }
-          e0 = __reduce_add_sync(0xffffffffu, e0 | (e1 << 16));  // e0, e1 <= oslots < 65536
-          e2 = __reduce_add_sync(0xffffffffu, e2);
-          if (lane == 0) {
-            atomicAdd(&s.stat[spar * 4 + 0], e0 & 0xFFFFu);
-            atomicAdd(&s.stat[spar * 4 + 1], e0 >> 16);
-            atomicAdd(&s.stat[spar * 4 + 2], e2);
-          }
-          for (uint32_t i = tid; i < p.tslots; i += NT) s.ctab[(st ^ 1) * p.tslots + i] = EMPTY;
-          if (tid < 4) s.stat[(spar ^ 1) * 4 + tid] = 0;
-          __syncthreads();  // B4
-          if (tid == 0) {
-            const uint32_t E0 = s.stat[spar * 4 + 0], E1 = s.stat[spar * 4 + 1], E2 = s.stat[spar * 4 + 2];
-            RbRegionVote vt;
-            vt.use_all = use_all ? 1u : 0u;
-            vt.n_prev = prev_n; vt.n_curr = cA.x; vt.w2_prev = prev_w2; vt.w2_curr = cA.y;
-            vt.nbins = nbins;
-            vt.nticket = nbins < rv ? nbins : rv;
-            const uint32_t gk[3] = {g0, g1, g2}, ck[3] = {c0, c1, c2};
-            // bins with a larger / larger-or-equal count than ticket k (counts are sorted c0 >= c1 >= c2)
-            uint32_t ngt[3], nge[3];
-            ngt[0] = 0; nge[0] = E0;
-            ngt[1] = c1 == c0 ? 0u : nge[0]; nge[1] = ngt[1] + E1;
-            ngt[2] = c2 == c1 ? ngt[1] : nge[1]; nge[2] = ngt[2] + E2;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-              RbBin b; b.dx = 0; b.dy = 0; b.cnt = 0;
-              vt.ticket[k] = b; vt.ngt[k] = 0; vt.nge[k] = 0;
-              if (k < 3 && k < vt.nticket) {
-                const uint32_t oid = offmask - (gk[k] & offmask);
-                vt.ticket[k].dx = (int32_t)(oid >> p.dybits) - (int32_t)g.W;
-                vt.ticket[k].dy = (int32_t)(oid & ((1u << p.dybits) - 1u)) - (int32_t)g.H;
-                vt.ticket[k].cnt = ck[k];
-                vt.ngt[k] = ngt[k]; vt.nge[k] = nge[k];
-              }
-            }
-            p.votes[(uint64_t)pairidx * g.nreg + region] = vt;
-          }
-          spar ^= 1;
-        } else {
-          // the pair cannot be finished here (a list or the offset table does not fit): defer it
-          if (tid == 0) {
-            const uint32_t at = atomicAdd(p.deferred_count, 1u);
-            if (at < p.deferred_cap) p.deferred[at] = make_uint2(pairidx, region);
-          }
-          for (uint32_t i = tid; i < p.oslots; i += NT) s.otab[i] = EMPTY;
-          for (uint32_t i = tid; i < p.tslots; i += NT) s.ctab[(st ^ 1) * p.tslots + i] = EMPTY;
-          if (tid < 4) s.stat[(spar ^ 1) * 4 + tid] = 0;
-          __syncthreads();
-          if (tid < 4) s.stat[spar * 4 + tid] = 0;
-          spar ^= 1;
-        }
-      }
-      prev_valid = fits;
-      prev_n = cA.x; prev_w2 = cA.y;
-      use_all = use_all_next;
-      cA = cB; cB = cC;
+      __syncthreads();  // votes of this step complete; tile[st] / plist[st] consumed; last step's ballot written
+      if (tid == 0 && t + 2 < nsteps) request(t + 2);
     }
-    // leave both code tables clean for the next work item (the last frame's table is still filled)
-    __syncthreads();
-    for (uint32_t i = tid; i < 2 * p.tslots; i += NT) s.ctab[i] = EMPTY;
-    __syncthreads();
+    // run finished: the ballot warp still owes the last pair; the next work item's first barrier waits for it
+    if (ballot_warp && nsteps >= 2) make_ballot(nsteps - 1, fa, region);
+    // bucket tables: the two built last are still filled
+    if (!ballot_warp) {
+      const uint32_t t1 = tb >= 1 ? tb - 1 : 2, t2 = t1 >= 1 ? t1 - 1 : 2;
+      uint4* h1 = reinterpret_cast<uint4*>(s.head + t1 * p.tslots);
+      uint4* h2 = reinterpret_cast<uint4*>(s.head + t2 * p.tslots);
+      for (uint32_t i = tid; i < p.tslots / 4; i += NTP) { h1[i] = make_uint4(NIL, NIL, NIL, NIL); h2[i] = make_uint4(NIL, NIL, NIL, NIL); }
+    }
   }
 }
 
