@@ -344,6 +344,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     if (cap > cntmax) cap = cntmax;  // a bin's count never exceeds the shorter list
     cap &= ~3u;                      // 16-byte list rows
     f.cap = cap;
+    f.lcap = 2 * cap;  // list rows hold all keypoints of a region even when only the weight-2 ones take part
     f.tslots = next_pow2(2 * cap < 64 ? 64 : 2 * cap);
     f.oslots = 1024;
     f.run = cfg->run_pairs ? cfg->run_pairs : 32;
@@ -359,7 +360,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
       RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_kpm_fast_kernel, RB_FAST_NT, c->fast_smem));
       c->fast_ctas_per_sm = occ < 1 ? 1 : occ;
       RB_CUDA(c, dmalloc(c, &c->d_frames4, c->frame_stride4 * N + 256));
-      RB_CUDA(c, dmalloc(c, &c->d_lists, (size_t)N * g.nreg * cap * 4 + 256));
+      RB_CUDA(c, dmalloc(c, &c->d_lists, (size_t)N * g.nreg * f.lcap * 4 + 256));
       RB_CUDA(c, dmalloc(c, &c->d_counts, (size_t)N * g.nreg * sizeof(uint2)));
       RB_CUDA(c, dmalloc(c, &c->d_deferred, (size_t)N * g.nreg * sizeof(uint2)));
       RB_CUDA(c, dmalloc(c, &c->d_work, 256));
@@ -551,7 +552,7 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
       // whatever K2 deferred (normally nothing: the grid exits on an empty list)
       const uint32_t items = (uint32_t)n * g.nreg;
       uint32_t lblocks = (items + 7) / 8;
-      rb_list_kernel<<<lblocks, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)first, (uint32_t)n, c->fast.cap, c->d_lists,
+      rb_list_kernel<<<lblocks, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)first, (uint32_t)n, c->fast.lcap, c->d_lists,
                                                     c->d_counts);
       RB_LAUNCHED(c, "rb_list_kernel");
       RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));  // work counter, deferred count, error word

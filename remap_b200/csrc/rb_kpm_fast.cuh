@@ -42,11 +42,12 @@
 
 struct RbKpmFastParams {
   RbGeom g;
-  const uint32_t* lists;   // [frame][region][cap]  (rb_prep.cuh)
+  const uint32_t* lists;   // [frame][region][lcap]  (rb_prep.cuh)
   const uint2* counts;     // [frame][region] (n_all, n_w2)
   RbRegionVote* votes;     // [npairs][nreg]
   uint32_t first_frame, npairs;
-  uint32_t cap;            // list capacity (<= 2047)
+  uint32_t cap;            // entries of one frame's region that can take part (shared-memory lists, <= 2047)
+  uint32_t lcap;           // entries per row of `lists` (>= cap, multiple of 4); a row is complete iff n_all <= lcap
   uint32_t tslots;         // code table slots, power of two >= 2 * cap
   uint32_t oslots;         // offset table slots, power of two
   uint32_t run;            // pairs per work item
@@ -120,9 +121,9 @@ struct Smem {           // stage k of a per-frame array lives at base + k * stri
   uint32_t tile_stride, plist_stride;  // bytes / words between the stages
 };
 
-// plan word of step t (frame fa + t): entries taking part | flags | n_all of the frame
+// plan word of step t (frame fa + t): entries taking part | flags | weight-2 entries of the frame
 constexpr uint32_t PLAN_LMASK = 0x7FFu, PLAN_FITS = 1u << 11, PLAN_PAIR_OK = 1u << 12, PLAN_USE_ALL = 1u << 13;
-constexpr uint32_t PLAN_NALL_SHIFT = 16;
+constexpr uint32_t PLAN_NW2_SHIFT = 16;
 
 __host__ __device__ inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -334,30 +335,35 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
       const uint2* cnts = p.counts + (uint64_t)fa * g.nreg + region;
       const uint32_t t = tid, ws = g.weight_switch;
       auto load = [&](int k) { return k >= 0 && k < (int)nsteps ? __ldg(cnts + (uint64_t)k * g.nreg) : make_uint2(0, 0); };
-      const uint2 cm2 = load((int)t - 2), cm1 = load((int)t - 1), c0 = load((int)t), cp1 = load((int)t + 1);
+      const uint2 cm1 = load((int)t - 1), c0 = load((int)t), cp1 = load((int)t + 1);
       // weight switch of a pair (a, b): src/kpm.hpp:219-220 ('<' on previous, '<=' on current)
       auto sw = [&](const uint2& a, const uint2& b) { return a.y < ws || b.y <= ws; };
-      const bool ua_m1 = t >= 2 && sw(cm2, cm1);               // pair (t - 2, t - 1)
       const bool ua_0 = t >= 1 && sw(cm1, c0);                 // pair (t - 1, t)
       const bool ua_p1 = t + 1 < nsteps && sw(c0, cp1);        // pair (t, t + 1)
       const uint32_t L = (ua_0 || ua_p1) ? c0.x : c0.y;        // entries of this frame that take part
-      const uint32_t Lm1 = (ua_m1 || ua_0) ? cm1.x : cm1.y;    // ... of the previous frame
-      const bool fits = L <= p.cap, fits_m1 = Lm1 <= p.cap;
-      uint32_t w = (fits ? (L | PLAN_FITS) : 0u) | (ua_0 ? PLAN_USE_ALL : 0u);
+      const uint32_t Lm1 = ((t >= 2 && sw(load((int)t - 2), cm1)) || ua_0) ? cm1.x : cm1.y;  // ... of the previous frame
+      // a list row is complete only if all of the region's keypoints fitted into it
+      const bool fits = c0.x <= p.lcap && L <= p.cap, fits_m1 = cm1.x <= p.lcap && Lm1 <= p.cap;
+      uint32_t w = (fits ? (L | PLAN_FITS | (c0.y << PLAN_NW2_SHIFT)) : 0u) | (ua_0 ? PLAN_USE_ALL : 0u);
       if (t >= 1 && fits && fits_m1) w |= PLAN_PAIR_OK;
-      const uint32_t nall = c0.x < p.cap ? c0.x : p.cap;
-      s.plan[t] = w | (nall << PLAN_NALL_SHIFT);
+      s.plan[t] = w;
     }
     __syncthreads();
 
     auto request = [&](uint32_t t) {  // thread 0 only: tile + list of step t into stage t & 1
-      const uint32_t stage = t & 1, frame = fa + t;
-      const uint32_t lbytes = ((s.plan[t] >> PLAN_NALL_SHIFT) * 4 + 15) & ~15u;
-      mbar_expect_tx(&s.mbar[stage], p.box_x * p.box_y * p.nbox_y + lbytes);
+      const uint32_t stage = t & 1, frame = fa + t, w = s.plan[t];
+      // weight-2 entries sit at the front of the list row, weight-1 entries (if this frame needs them) at its end
+      const uint32_t L = w & PLAN_LMASK, nw2 = (w >> PLAN_NW2_SHIFT) & PLAN_LMASK;
+      const uint32_t bytes2 = (w & PLAN_FITS) ? (nw2 * 4 + 15) & ~15u : 0u;
+      const uint32_t a1 = (p.cap - (L - nw2)) & ~3u;  // shared-memory index; the row's index is a1 + lcap - cap
+      const uint32_t bytes1 = ((w & PLAN_FITS) && L > nw2) ? (p.cap - a1) * 4 : 0u;
+      mbar_expect_tx(&s.mbar[stage], p.box_x * p.box_y * p.nbox_y + bytes2 + bytes1);
       for (uint32_t b = 0; b < p.nbox_y; ++b)
         tma_load_3d(s.tile + stage * s.tile_stride + b * p.box_x * p.box_y, &tmap, tx0 / 2, Y0 - 2 + b * p.box_y, frame,
                     &s.mbar[stage]);
-      if (lbytes) bulk_load(s.plist + stage * s.plist_stride, p.lists + ((uint64_t)frame * g.nreg + region) * p.cap, lbytes, &s.mbar[stage]);
+      const uint32_t* row = p.lists + ((uint64_t)frame * g.nreg + region) * p.lcap;
+      if (bytes2) bulk_load(s.plist + stage * s.plist_stride, row, bytes2, &s.mbar[stage]);
+      if (bytes1) bulk_load(s.plist + stage * s.plist_stride + a1, row + a1 + (p.lcap - p.cap), bytes1, &s.mbar[stage]);
     };
     if (tid == 0) {
       request(0);
@@ -380,7 +386,7 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
 
         // ---- codes, build this frame's buckets, probe the previous frame's, vote -------------------
         if (w & PLAN_FITS) {
-          const uint32_t L = w & PLAN_LMASK;
+          const uint32_t L = w & PLAN_LMASK, nw2 = (w >> PLAN_NW2_SHIFT) & PLAN_LMASK;
           const bool pair_ok = (w & PLAN_PAIR_OK) != 0, use_all = (w & PLAN_USE_ALL) != 0;
           const uint32_t tmask = p.tslots - 1, omask = p.oslots - 1, cntbits = 32 - p.offbits, wpr = p.box_x / 4;
           const uint32_t* tile = reinterpret_cast<const uint32_t*>(s.tile + st * s.tile_stride);
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
           for (uint32_t i = tid; i < Lw; i += NTP) {
             uint32_t oid0 = NONE | lane, oid1 = NONE | lane;  // unique per lane: groups of one in match_any
             if (i < L) {
-              const uint32_t pos = plist[i];
+              const uint32_t pos = plist[i < nw2 ? i : p.cap - 1 - (i - nw2)];
               const uint32_t x = pos & 0x7FFFu, y = pos >> 16;
               const Code c = code_at(tile, wpr, x - 2 - tx0, y - Y0);
               const uint32_t slot = code_hash(c) & tmask;

@@ -8,11 +8,12 @@
 //                        src/kpr.hpp:71-74), with the region's weight counts
 //                        (kpr::region::add, src/kpr.hpp:121-124).
 //
-// List layout: lists[(frame * nreg + region) * cap + i] = x | w2 << 15 | y << 16, the weight-2
-// keypoints first (row-major), then the weight-1 ones, so that a pair whose weight switch
-// (src/kpm.hpp:219-220) selects weight-2 codes only reads a prefix.  counts[frame * nreg + region] =
-// (n_all, n_w2).  Entries beyond `cap` are dropped; the matcher sees n > cap in `counts` and hands
-// such a region to the general kernel (rb_kpm.cuh), which works from the bit maps.
+// List layout: row (frame * nreg + region) of `lists` has `cap` entries x | w2 << 15 | y << 16: the
+// weight-2 keypoints in entries [0, n_w2) and the weight-1 keypoints in entries (cap - 1 - m), m = 0 ..
+// n_w1 - 1, so that a pair whose weight switch (src/kpm.hpp:219-220) selects weight-2 codes only reads
+// a prefix.  counts[frame * nreg + region] = (n_all, n_w2).  When n_all > cap the row is incomplete; the
+// matcher sees that in `counts` and hands such a region to the general kernel (rb_kpm.cuh), which works
+// from the bit maps.
 #pragma once
 
 #include "rb_common.cuh"
@@ -54,7 +55,10 @@ __device__ __forceinline__ uint32_t colmask(uint32_t X0, uint32_t X1, uint32_t j
 
 }  // namespace rbl
 
-// One warp per (frame, region).
+// One warp per (frame, region), one pass over the region's bit-map words.  Lanes are laid out as
+// (row within the chunk, strip), floor(32 / nstr) rows per chunk, so a lane's strip and column mask never
+// change and its row advances by a constant.  Weight-2 keypoints are written forward from entry 0, weight-1
+// keypoints backward from entry cap - 1; with n_all <= cap the two blocks never meet.
 __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint32_t* __restrict__ kpbits,
                                                       const uint32_t* __restrict__ w2bits, uint32_t first_frame,
                                                       uint32_t nframes, uint32_t cap, uint32_t* __restrict__ lists,
@@ -67,66 +71,53 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
     const uint32_t cs = region / g.grid_h, rs = region % g.grid_h;
     const uint32_t X0 = g.col0[cs], X1 = g.col1[cs], Y0 = g.row0[rs], Y1 = g.row1[rs];
     const uint32_t j0 = (X0 - 2) / RB_STRIP_OUT, j1 = (X1 - 1 - 2) / RB_STRIP_OUT, nstr = j1 - j0 + 1;
-    const uint32_t nwords = (Y1 - Y0) * nstr;
-    const uint64_t base = ((uint64_t)frame * g.H + Y0) * g.NS + j0;
-    // pass 1: totals (loads batched four deep: the loop is latency-bound otherwise)
-    uint32_t ca = 0, cb = 0;
-    for (uint32_t i0 = lane; i0 < nwords; i0 += 128) {
-      uint32_t kw[4], ww[4], m[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = i0 + 32 * u;
-        kw[u] = ww[u] = m[u] = 0;
-        if (i < nwords) {
-          const uint32_t row = i / nstr, k = i - row * nstr;
-          m[u] = rbl::colmask(X0, X1, j0 + k);
-          kw[u] = __ldg(kpbits + base + (uint64_t)row * g.NS + k);
-          ww[u] = __ldg(w2bits + base + (uint64_t)row * g.NS + k);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { ca += __popc(kw[u] & m[u]); cb += __popc(ww[u] & m[u]); }
-    }
-    const uint32_t n_all = __reduce_add_sync(0xffffffffu, ca), n_w2 = __reduce_add_sync(0xffffffffu, cb);
-    if (lane == 0) counts[(uint64_t)frame * g.nreg + region] = make_uint2(n_all, n_w2);
-    // pass 2: emit, weight 2 from 0, weight 1 from n_w2
+    // lanes = (row within the chunk, strip): floor(32 / nstr) rows per chunk, fixed for the whole region
+    const uint32_t rpc = nstr <= 32 ? 32u / nstr : 0u;
+    const uint32_t r0 = nstr <= 32 ? lane / nstr : 0u, k = lane - r0 * nstr;
+    const uint32_t nrows = Y1 - Y0;
+    const uint32_t* kp = kpbits + ((uint64_t)frame * g.H + Y0) * g.NS + j0 + k;
+    const uint32_t* w2 = w2bits + ((uint64_t)frame * g.H + Y0) * g.NS + j0 + k;
     uint32_t* out = lists + ((uint64_t)frame * g.nreg + region) * cap;
-    uint32_t b2 = 0, b1 = n_w2;
-    for (uint32_t i0 = 0; i0 < nwords; i0 += 32) {
-      const uint32_t i = i0 + lane;
-      uint32_t kw = 0, ww = 0, row = 0, k = 0;
-      if (i < nwords) {
-        row = i / nstr; k = i - row * nstr;
-        const uint32_t m = rbl::colmask(X0, X1, j0 + k);
-        kw = __ldg(kpbits + base + (uint64_t)row * g.NS + k) & m;
-        ww = __ldg(w2bits + base + (uint64_t)row * g.NS + k) & m;
-      }
-      uint32_t w1 = kw & ~ww;
-      const uint32_t c = __popc(ww) | (__popc(w1) << 16);  // both counts in one word
-      uint32_t incl = c;
+    uint32_t b2 = 0, b1 = 0;
+    if (rpc != 0) {
+      const uint32_t m = r0 < rpc ? rbl::colmask(X0, X1, j0 + k) : 0u;
+      const uint32_t xb = RB_STRIP_OUT * (j0 + k);
+      uint32_t row = r0;
+      uint32_t kw = 0, ww = 0;
+      if (m != 0 && row < nrows) { kw = __ldg(kp + (uint64_t)row * g.NS); ww = __ldg(w2 + (uint64_t)row * g.NS); }
+      for (uint32_t ra = 0; ra < nrows; ra += rpc) {
+        // prefetch the next chunk's words before working on this one
+        const uint32_t nrow = row + rpc;
+        uint32_t nkw = 0, nww = 0;
+        if (m != 0 && nrow < nrows) { nkw = __ldg(kp + (uint64_t)nrow * g.NS); nww = __ldg(w2 + (uint64_t)nrow * g.NS); }
+        kw &= m; ww &= m;
+        const uint32_t c = __popc(ww) | (__popc(kw & ~ww) << 16);  // weight-2 / weight-1 counts in one word
+        uint32_t incl = c;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+          if ((int)lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - c, tot = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t at2 = b2 + (excl & 0xFFFFu), at1 = cap - 1 - (b1 + (excl >> 16));  // weight 1 runs backward
+        const uint32_t yv = ((Y0 + row) << 16) + xb;
+        while (kw) {
+          const uint32_t b = __ffs((int)kw) - 1;
+          kw &= kw - 1;
+          const bool is2 = (ww >> b) & 1u;
+          const uint32_t at = is2 ? at2 : at1;
+          if (at < cap) out[at] = (yv + b) | (is2 ? 0x8000u : 0u);  // at1 wraps far above cap when the row is full
+          at2 += is2 ? 1u : 0u;
+          at1 -= is2 ? 0u : 1u;
+        }
+        b2 += tot & 0xFFFFu;
+        b1 += tot >> 16;
+        kw = nkw; ww = nww; row = nrow;
       }
-      const uint32_t excl = incl - c, tot = __shfl_sync(0xffffffffu, incl, 31);
-      uint32_t at2 = b2 + (excl & 0xFFFFu), at1 = b1 + (excl >> 16);
-      const uint32_t y = Y0 + row, xb = RB_STRIP_OUT * (j0 + k);
-      while (ww) {
-        const uint32_t b = __ffs((int)ww) - 1;
-        ww &= ww - 1;
-        if (at2 < cap) out[at2] = (xb + b) | 0x8000u | (y << 16);
-        ++at2;
-      }
-      while (w1) {
-        const uint32_t b = __ffs((int)w1) - 1;
-        w1 &= w1 - 1;
-        if (at1 < cap) out[at1] = (xb + b) | (y << 16);
-        ++at1;
-      }
-      b2 += tot & 0xFFFFu;
-      b1 += tot >> 16;
+    } else {
+      b2 = b1 = cap + 1;  // a region wider than 32 strips: leave it to the general kernel
     }
+    if (lane == 0) counts[(uint64_t)frame * g.nreg + region] = make_uint2(b2 + b1, b2);
   }
 }
 
