@@ -8,7 +8,7 @@
 //                        src/kpr.hpp:71-74), with the region's weight counts
 //                        (kpr::region::add, src/kpr.hpp:121-124).
 //
-// List layout: row (frame * nreg + region) of `lists` has `cap` entries x | w2 << 15 | y << 16: the
+// K1c list layout: row (frame * nreg + region) of `lists` has `cap` entries x | w2 << 15 | y << 16: the
 // weight-2 keypoints in entries [0, n_w2) and the weight-1 keypoints in entries (cap - 1 - m), m = 0 ..
 // n_w1 - 1, so that a pair whose weight switch (src/kpm.hpp:219-220) selects weight-2 codes only reads
 // a prefix.  counts[frame * nreg + region] = (n_all, n_w2).  When n_all > cap the row is incomplete; the
@@ -17,6 +17,78 @@
 #pragma once
 
 #include "rb_common.cuh"
+
+// ---- K1c: one warp per (frame, region), one pass over the region's bit-map words ---------------
+// Lanes are laid out as (row within the chunk, strip), floor(32 / nstr) rows per chunk, so a lane's
+// strip and column mask never change and its row advances by a constant.  Per chunk: every lane
+// counts the keypoints of its word, one warp scan turns the counts into write positions, every lane
+// emits its word.  Weight-2 keypoints are written forward from entry 0, weight-1 keypoints backward
+// from entry cap - 1; with n_all <= cap the two blocks never meet.
+// The lane functions are host+device so that tests/emul can run them lane by lane.
+struct RbListLane {
+  uint32_t Y0, nrows, j, nstr, rows_per_chunk, row0;  // the lane's word of chunk c: row row0 + c * rows_per_chunk
+  uint32_t mask;                                      // column mask of its strip (0: idle lane)
+};
+
+namespace rbl {
+
+// bits of strip word j (bit i <-> x = 28 j + i, outputs at bits 2..29) that lie in [X0, X1)
+RB_HD uint32_t colmask(uint32_t X0, uint32_t X1, uint32_t j) {
+  const int lo = (int)X0 - (int)(RB_STRIP_OUT * j), hi = (int)X1 - (int)(RB_STRIP_OUT * j);
+  if (lo >= 30 || hi <= 2) return 0u;
+  uint32_t m = 0x3FFFFFFCu;
+  if (lo > 2) m &= ~((1u << lo) - 1u);
+  if (hi < 30) m &= (1u << hi) - 1u;
+  return m;
+}
+
+RB_HD RbListLane lane_setup(const RbGeom& g, uint32_t region, uint32_t lane) {
+  RbListLane L;
+  const uint32_t cs = region / g.grid_h, rs = region % g.grid_h;
+  const uint32_t X0 = g.col0[cs], X1 = g.col1[cs];
+  L.Y0 = g.row0[rs]; L.nrows = g.row1[rs] - g.row0[rs];
+  const uint32_t j0 = (X0 - 2) / RB_STRIP_OUT, j1 = (X1 - 1 - 2) / RB_STRIP_OUT;
+  L.nstr = j1 - j0 + 1;
+  L.mask = 0; L.j = j0; L.row0 = 0; L.rows_per_chunk = 0;
+  if (L.nstr > 32) return L;  // wider than a warp: counts are forced above cap, the matcher defers
+  L.rows_per_chunk = 32u / L.nstr;
+  const uint32_t r = lane / L.nstr, k = lane - r * L.nstr;
+  if (r >= L.rows_per_chunk) return L;
+  L.j = j0 + k;
+  L.row0 = r;
+  L.mask = colmask(X0, X1, L.j);
+  return L;
+}
+
+// the lane's masked words of the chunk that starts at region row `ra`
+RB_HD void lane_words(const RbGeom& g, const RbListLane& L, const uint32_t* kpf, const uint32_t* w2f, uint32_t ra,
+                      uint32_t& kw, uint32_t& ww) {
+  kw = ww = 0;
+  const uint32_t row = ra + L.row0;
+  if (L.mask && row < L.nrows) {
+    const uint64_t at = (uint64_t)(L.Y0 + row) * g.NS + L.j;
+    kw = kpf[at] & L.mask;
+    ww = w2f[at] & L.mask;
+  }
+}
+
+// at2 / n1_before: weight-2 / weight-1 keypoints of the region before this lane's word
+RB_HD void lane_emit(const RbListLane& L, uint32_t ra, uint32_t kw, uint32_t ww, uint32_t at2, uint32_t n1_before,
+                     uint32_t cap, uint32_t* out) {
+  uint32_t at1 = cap - 1 - n1_before;  // wraps far above cap when the row is full
+  const uint32_t yv = ((L.Y0 + ra + L.row0) << 16) + RB_STRIP_OUT * L.j;
+  while (kw) {
+    const uint32_t b = rb_ffs0(kw);
+    kw &= kw - 1;
+    const bool is2 = (ww >> b) & 1u;
+    const uint32_t at = is2 ? at2 : at1;
+    if (at < cap) out[at] = (yv + b) | (is2 ? 0x8000u : 0u);
+    at2 += is2 ? 1u : 0u;
+    at1 -= is2 ? 0u : 1u;
+  }
+}
+
+}  // namespace rbl
 
 #if defined(__CUDACC__)
 
@@ -42,23 +114,6 @@ __global__ void __launch_bounds__(256) rb_pack_kernel(const uint8_t* __restrict_
   }
 }
 
-namespace rbl {
-
-// bits of strip word j (bit i <-> x = 28 j + i, outputs at bits 2..29) that lie in [X0, X1)
-__device__ __forceinline__ uint32_t colmask(uint32_t X0, uint32_t X1, uint32_t j) {
-  const int lo = (int)X0 - (int)(RB_STRIP_OUT * j), hi = (int)X1 - (int)(RB_STRIP_OUT * j);
-  uint32_t m = 0x3FFFFFFCu;
-  if (lo > 2) m &= ~((1u << lo) - 1u);
-  if (hi < 30) m &= (1u << (hi < 0 ? 0 : hi)) - 1u;
-  return m;
-}
-
-}  // namespace rbl
-
-// One warp per (frame, region), one pass over the region's bit-map words.  Lanes are laid out as
-// (row within the chunk, strip), floor(32 / nstr) rows per chunk, so a lane's strip and column mask never
-// change and its row advances by a constant.  Weight-2 keypoints are written forward from entry 0, weight-1
-// keypoints backward from entry cap - 1; with n_all <= cap the two blocks never meet.
 __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint32_t* __restrict__ kpbits,
                                                       const uint32_t* __restrict__ w2bits, uint32_t first_frame,
                                                       uint32_t nframes, uint32_t cap, uint32_t* __restrict__ lists,
@@ -68,29 +123,17 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
   const uint32_t nitems = nframes * g.nreg;
   for (uint32_t item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < nitems; item += gridDim.x * warps_per_block) {
     const uint32_t frame = first_frame + item / g.nreg, region = item % g.nreg;
-    const uint32_t cs = region / g.grid_h, rs = region % g.grid_h;
-    const uint32_t X0 = g.col0[cs], X1 = g.col1[cs], Y0 = g.row0[rs], Y1 = g.row1[rs];
-    const uint32_t j0 = (X0 - 2) / RB_STRIP_OUT, j1 = (X1 - 1 - 2) / RB_STRIP_OUT, nstr = j1 - j0 + 1;
-    // lanes = (row within the chunk, strip): floor(32 / nstr) rows per chunk, fixed for the whole region
-    const uint32_t rpc = nstr <= 32 ? 32u / nstr : 0u;
-    const uint32_t r0 = nstr <= 32 ? lane / nstr : 0u, k = lane - r0 * nstr;
-    const uint32_t nrows = Y1 - Y0;
-    const uint32_t* kp = kpbits + ((uint64_t)frame * g.H + Y0) * g.NS + j0 + k;
-    const uint32_t* w2 = w2bits + ((uint64_t)frame * g.H + Y0) * g.NS + j0 + k;
+    const RbListLane L = rbl::lane_setup(g, region, lane);
+    const uint32_t* kpf = kpbits + (uint64_t)frame * g.H * g.NS;
+    const uint32_t* w2f = w2bits + (uint64_t)frame * g.H * g.NS;
     uint32_t* out = lists + ((uint64_t)frame * g.nreg + region) * cap;
     uint32_t b2 = 0, b1 = 0;
-    if (rpc != 0) {
-      const uint32_t m = r0 < rpc ? rbl::colmask(X0, X1, j0 + k) : 0u;
-      const uint32_t xb = RB_STRIP_OUT * (j0 + k);
-      uint32_t row = r0;
-      uint32_t kw = 0, ww = 0;
-      if (m != 0 && row < nrows) { kw = __ldg(kp + (uint64_t)row * g.NS); ww = __ldg(w2 + (uint64_t)row * g.NS); }
-      for (uint32_t ra = 0; ra < nrows; ra += rpc) {
-        // prefetch the next chunk's words before working on this one
-        const uint32_t nrow = row + rpc;
-        uint32_t nkw = 0, nww = 0;
-        if (m != 0 && nrow < nrows) { nkw = __ldg(kp + (uint64_t)nrow * g.NS); nww = __ldg(w2 + (uint64_t)nrow * g.NS); }
-        kw &= m; ww &= m;
+    if (L.rows_per_chunk != 0) {
+      uint32_t kw, ww;
+      rbl::lane_words(g, L, kpf, w2f, 0, kw, ww);
+      for (uint32_t ra = 0; ra < L.nrows; ra += L.rows_per_chunk) {
+        uint32_t nkw, nww;  // next chunk's words, requested before this chunk is worked on
+        rbl::lane_words(g, L, kpf, w2f, ra + L.rows_per_chunk, nkw, nww);
         const uint32_t c = __popc(ww) | (__popc(kw & ~ww) << 16);  // weight-2 / weight-1 counts in one word
         uint32_t incl = c;
 #pragma unroll
@@ -99,23 +142,13 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
           if ((int)lane >= o) incl += t;
         }
         const uint32_t excl = incl - c, tot = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t at2 = b2 + (excl & 0xFFFFu), at1 = cap - 1 - (b1 + (excl >> 16));  // weight 1 runs backward
-        const uint32_t yv = ((Y0 + row) << 16) + xb;
-        while (kw) {
-          const uint32_t b = __ffs((int)kw) - 1;
-          kw &= kw - 1;
-          const bool is2 = (ww >> b) & 1u;
-          const uint32_t at = is2 ? at2 : at1;
-          if (at < cap) out[at] = (yv + b) | (is2 ? 0x8000u : 0u);  // at1 wraps far above cap when the row is full
-          at2 += is2 ? 1u : 0u;
-          at1 -= is2 ? 0u : 1u;
-        }
+        rbl::lane_emit(L, ra, kw, ww, b2 + (excl & 0xFFFFu), b1 + (excl >> 16), cap, out);
         b2 += tot & 0xFFFFu;
         b1 += tot >> 16;
-        kw = nkw; ww = nww; row = nrow;
+        kw = nkw; ww = nww;
       }
     } else {
-      b2 = b1 = cap + 1;  // a region wider than 32 strips: leave it to the general kernel
+      b2 = b1 = cap + 1;  // not listed: forces the matcher to defer this region
     }
     if (lane == 0) counts[(uint64_t)frame * g.nreg + region] = make_uint2(b2 + b1, b2);
   }

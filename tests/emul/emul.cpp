@@ -14,6 +14,7 @@
 #define RB_EMUL 1
 #include "../../remap_b200/csrc/rb_host.hpp"
 #include "../../remap_b200/csrc/rb_kpe.cuh"
+#include "../../remap_b200/csrc/rb_prep.cuh"
 
 extern "C" {
 
@@ -45,6 +46,35 @@ int emul_kpe(const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, uint32_t
       for (uint32_t y = 0; y < H; ++y)
         memcpy(median + ((size_t)f * H + y) * W, &dmed[f * g.median_stride + (size_t)y * g.mpitch + 2], W);
   return (int)g.NS;
+}
+
+// K1c (rb_prep.cuh): the lane functions of rb_list_kernel run lane by lane, with the warp scan done
+// serially here.  kp / w2: n*H*NS words (from emul_kpe).  lists: n*8*cap words, counts: n*8*2 words.
+int emul_lists(const uint32_t* kp, const uint32_t* w2, uint32_t n, uint32_t W, uint32_t H, uint32_t cap, uint32_t* lists,
+               uint32_t* counts) {
+  RbGeom g;
+  if (rb_make_geom(W, H, 4, 2, 16, 10, 3, &g) != 0) return -1;
+  memset(lists, 0xFF, (size_t)n * g.nreg * cap * 4);
+  for (uint32_t f = 0; f < n; ++f)
+    for (uint32_t r = 0; r < g.nreg; ++r) {
+      const uint32_t* kpf = kp + (size_t)f * H * g.NS;
+      const uint32_t* w2f = w2 + (size_t)f * H * g.NS;
+      RbListLane L[32];
+      uint32_t a2 = 0, a1 = 0;
+      for (uint32_t lane = 0; lane < 32; ++lane) L[lane] = rbl::lane_setup(g, r, lane);
+      if (L[0].rows_per_chunk == 0) { a2 = a1 = cap + 1; }
+      else
+        for (uint32_t ra = 0; ra < L[0].nrows; ra += L[0].rows_per_chunk)
+          for (uint32_t lane = 0; lane < 32; ++lane) {  // lanes in order == the warp's exclusive scan
+            uint32_t kw, ww;
+            rbl::lane_words(g, L[lane], kpf, w2f, ra, kw, ww);
+            rbl::lane_emit(L[lane], ra, kw, ww, a2, a1, cap, lists + ((size_t)f * g.nreg + r) * cap);
+            a2 += (uint32_t)__builtin_popcount(ww); a1 += (uint32_t)__builtin_popcount(kw & ~ww);
+          }
+      counts[((size_t)f * g.nreg + r) * 2] = a2 + a1;
+      counts[((size_t)f * g.nreg + r) * 2 + 1] = a2;
+    }
+  return (int)g.nreg;
 }
 
 uint32_t emul_strips(uint32_t W) { return (W - 4 + RB_STRIP_OUT - 1) / RB_STRIP_OUT; }

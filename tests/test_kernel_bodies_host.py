@@ -119,3 +119,28 @@ def test_match_vote_declare_bodies(name):
     _, k0 = oracle.extract(cfg, frames[tp])
     _, k1 = oracle.extract(cfg, frames[tp + 1])
     assert np.array_equal(bins, oracle.region_bins(cfg, k0, k1, tr))
+
+
+@pytest.mark.parametrize("name,cap", [("scroll", 2048), ("odd", 2048), ("random", 2048), ("wide", 4096), ("scroll", 300)])
+def test_region_list_body(name, cap):
+    """K1c (rb_list_kernel's lane functions): per-(frame, region) keypoint lists == the oracle's keypoints
+    filtered by region mask; weight-2 entries from the front, weight-1 entries from the back."""
+    frames = KPE_CASES[name]()
+    L = emul_build.lib()
+    n, H, W = frames.shape
+    _, kp, w2 = emul_kpe(frames, 1)
+    lists = np.zeros((n, 8, cap), np.uint32)
+    counts = np.zeros((n, 8, 2), np.uint32)
+    assert L.emul_lists(P(kp), P(w2), n, W, H, cap, P(lists), P(counts)) == 8
+    cfg = oracle.config(W, H)
+    for f in range(n):
+        _, okps = oracle.extract(cfg, frames[f])
+        for r in range(8):
+            sel = okps[(okps["region_mask"] >> r) & 1 == 1]
+            want2 = sorted((int(k["x"]) | 0x8000 | int(k["y"]) << 16) for k in sel if k["weight"] == 2)
+            want1 = sorted((int(k["x"]) | int(k["y"]) << 16) for k in sel if k["weight"] == 1)
+            nall, n2 = int(counts[f, r, 0]), int(counts[f, r, 1])
+            assert (nall, n2) == (len(want1) + len(want2), len(want2)), (name, f, r)
+            if nall <= cap:  # a fuller row is incomplete by contract: the matcher defers that region
+                assert sorted(int(v) for v in lists[f, r, :n2]) == want2
+                assert sorted(int(v) for v in lists[f, r, cap - (nall - n2):]) == want1
