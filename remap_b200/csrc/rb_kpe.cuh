@@ -112,40 +112,43 @@ RB_HD void thresholds(const uint32_t o[4], uint32_t T[15]) {
 }
 
 // One threshold plane, five consecutive rows t4 (y-2) .. t0 (y+2) -> q3 = [3x3 count >= 4],
-// q5 = [5x5 count >= 12] for the 32 pixels of the word (bits 2..29 are exact).
+// q5 = [5x5 count >= 12], both SHIFTED LEFT BY TWO: bit i of q3 / q5 belongs to pixel i - 2 of the
+// word (exact for bits 4..31).  All horizontal neighbours are taken with LEFT shifts only: ptxas
+// turns those into IMAD.SHL on the FMA pipe, which idles here, while right shifts (SHF.R) would
+// compete with the LOP3s for the ALU pipe that bounds this kernel (profiles/README.md, r1b).
 RB_HD void rank_planes(uint32_t t4, uint32_t t3, uint32_t t2, uint32_t t1, uint32_t t0, uint32_t& q3, uint32_t& q5) {
   // vertical sums: V3 = t3+t2+t1 = a1 a0 ; V5 = V3 + t4 + t0 = b2 b1 b0
   const uint32_t a0 = rb_xor3(t3, t2, t1), a1 = rb_maj(t3, t2, t1);
   const uint32_t b0 = rb_xor3(a0, t4, t0), c = rb_maj(a0, t4, t0);
   const uint32_t b1 = a1 ^ c, b2 = a1 & c;
-  // 3x3: count = u + 2 v, u = a0(x-1)+a0(x)+a0(x+1), v likewise on a1;  count >= 4 <=> v>=2 | (v>=1 & u>=2)
+  // 3x3: count = u + 2 v, u = a0(x-1)+a0(x)+a0(x+1), v likewise on a1;  count >= 4 <=> v>=2 | (v>=1 & u>=2).
+  // (a, a << 1, a << 2) centres the window on bit i - 1; one more shift brings it to i - 2.
   {
-    const uint32_t l0 = a0 << 1, r0 = a0 >> 1, l1 = a1 << 1, r1 = a1 >> 1;
-    q3 = rb_maj(l1, a1, r1) | ((l1 | a1 | r1) & rb_maj(l0, a0, r0));
+    const uint32_t m0 = a0 << 1, n0 = a0 << 2, m1 = a1 << 1, n1 = a1 << 2;
+    q3 = (rb_maj(a1, m1, n1) | ((a1 | m1 | n1) & rb_maj(a0, m0, n0))) << 1;
   }
-  // 5x5: S = U + 2 V + 4 W with U, V, W the 5-wide horizontal popcounts of b0, b1, b2
+  // 5x5: S = U + 2 V + 4 W with U, V, W the 5-wide horizontal popcounts of b0, b1, b2; columns i-4 .. i
   {
     // U: only its 2s and 4s bits matter for S >= 12
-    uint32_t e0 = b0 << 2, e1 = b0 << 1, e3 = b0 >> 1, e4 = b0 >> 2;
-    uint32_t s = rb_xor3(e0, e1, b0), k = rb_maj(e0, e1, b0), k2 = rb_maj(s, e3, e4);
+    uint32_t e1 = b0 << 1, e2 = b0 << 2, e3 = b0 << 3, e4 = b0 << 4;
+    uint32_t s = rb_xor3(b0, e1, e2), k = rb_maj(b0, e1, e2), k2 = rb_maj(s, e3, e4);
     const uint32_t u1 = k ^ k2, u2 = k & k2;
-    e0 = b1 << 2; e1 = b1 << 1; e3 = b1 >> 1; e4 = b1 >> 2;
-    s = rb_xor3(e0, e1, b1); k = rb_maj(e0, e1, b1);
+    e1 = b1 << 1; e2 = b1 << 2; e3 = b1 << 3; e4 = b1 << 4;
+    s = rb_xor3(b1, e1, e2); k = rb_maj(b1, e1, e2);
     const uint32_t v0 = rb_xor3(s, e3, e4);
     k2 = rb_maj(s, e3, e4);
     const uint32_t v1 = k ^ k2, v2 = k & k2;
-    e0 = b2 << 2; e1 = b2 << 1; e3 = b2 >> 1; e4 = b2 >> 2;
-    s = rb_xor3(e0, e1, b2); k = rb_maj(e0, e1, b2);
+    e1 = b2 << 1; e2 = b2 << 2; e3 = b2 << 3; e4 = b2 << 4;
+    s = rb_xor3(b2, e1, e2); k = rb_maj(b2, e1, e2);
     const uint32_t w0 = rb_xor3(s, e3, e4);
     k2 = rb_maj(s, e3, e4);
     const uint32_t w1 = k ^ k2, w2 = k & k2;
-    // bit1: u1 + v0 -> carry c1 ; bit2: u2 + v1 + w0 + c1 ; bit3: v2 + w1 + carries ; bit4+: w2 + carries
-    const uint32_t c1 = u1 & v0;
-    const uint32_t x = rb_xor3(u2, v1, w0), cx = rb_maj(u2, v1, w0);
-    const uint32_t s2 = x ^ c1, c2 = x & c1;
-    const uint32_t y = rb_xor3(v2, w1, cx), cy = rb_maj(v2, w1, cx);
-    const uint32_t s3 = y ^ c2, c3 = y & c2;
-    q5 = w2 | cy | c3 | (s3 & s2);  // S >= 16, or 12 <= S <= 15
+    // A column's count is <= 5, so its 2s and 4s bits are never both set: Z = V + 2 W <= 10 and
+    // S = U + 2 Z.  S >= 12  <=>  Z >= 6, or Z == 5 and U >= 2, or Z == 4 and U >= 4.
+    const uint32_t z1 = v1 ^ w0, k1 = v1 & w0;
+    const uint32_t z2 = rb_xor3(v2, w1, k1), z3 = w2 | rb_maj(v2, w1, k1);
+    const uint32_t ok45 = u2 | (v0 & u1);          // Z odd (== 5): U >= 2 ; Z even (== 4): U >= 4
+    q5 = z3 | (z2 & (z1 | ok45));                  // z3: Z >= 8 ; z2 & z1: Z in 6..7 ; z2 & !z1: Z in 4..5
   }
 }
 
@@ -195,20 +198,21 @@ RB_HD void strip_step(StripState& st, const uint32_t wnew[8], uint32_t vmask, ui
   uint32_t q3[15], q5[15];
 #pragma unroll
   for (int t = 0; t < 15; ++t) rank_planes(st.T[0][t], st.T[1][t], st.T[2][t], st.T[3][t], Tn[t], q3[t], q5[t]);
+  // q3 / q5 and everything derived from them live two bits to the left of the input planes
   uint32_t p3[4], p5[4];
   thermo_to_binary(q3, p3);
   thermo_to_binary(q5, p5);
-  const uint32_t* p1 = st.O[2];  // centre row
+  const uint32_t p1[4] = {st.O[2][0] << 2, st.O[2][1] << 2, st.O[2][2] << 2, st.O[2][3] << 2};  // centre row
   const uint32_t ne13 = (p1[0] ^ p3[0]) | (p1[1] ^ p3[1]) | (p1[2] ^ p3[2]) | (p1[3] ^ p3[3]);
   const uint32_t ne35 = (p3[0] ^ p5[0]) | (p3[1] ^ p5[1]) | (p3[2] ^ p5[2]) | (p3[3] ^ p5[3]);
   const uint32_t ne15 = (p1[0] ^ p5[0]) | (p1[1] ^ p5[1]) | (p1[2] ^ p5[2]) | (p1[3] ^ p5[3]);
-  const uint32_t kp = ne13 & ne35 & vmask;  // src/kpe.hpp:316-318
+  const uint32_t kp = (ne13 & ne35) >> 2 & vmask;  // src/kpe.hpp:316-318
   *kp_out = kp;
-  *w2_out = kp & ne15;                      // src/kpe.hpp:319
+  *w2_out = kp & (ne15 >> 2);               // src/kpe.hpp:319
   if (med_out) {
     uint32_t m[4], w[8];
-    m[0] = o2n_plane<0>(p3) & vmask; m[1] = o2n_plane<1>(p3) & vmask;
-    m[2] = o2n_plane<2>(p3) & vmask; m[3] = o2n_plane<3>(p3) & vmask;
+    m[0] = (o2n_plane<0>(p3) >> 2) & vmask; m[1] = (o2n_plane<1>(p3) >> 2) & vmask;
+    m[2] = (o2n_plane<2>(p3) >> 2) & vmask; m[3] = (o2n_plane<3>(p3) >> 2) & vmask;
     planes_to_bytes(m, w);
     uint32_t* dst = reinterpret_cast<uint32_t*>(med_out);  // pixel 28j+2 -> byte 28j+4 of the row
 #pragma unroll
