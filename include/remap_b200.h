@@ -59,6 +59,7 @@ typedef struct rb_config {
   uint32_t list_cap;        /* 0 = auto; per-region keypoint list capacity of the pipelined
                                matcher (<= 2047); longer lists are deferred                   */
   uint32_t run_pairs;       /* 0 = auto; consecutive pairs per work item of the matcher      */
+  uint32_t upload_chunk;    /* 0 = auto; frames per host->device chunk of rb_register_host_async */
 } rb_config;
 
 /* == std::optional<cdt::offset_t> returned by kpm::match (src/kpm.hpp:395-415), plus flags. */
@@ -113,6 +114,13 @@ int rb_upload(rb_ctx* ctx, const uint8_t* frames, size_t first, size_t n);
  * kernels on the context's stream and returns; results stay in HBM until fetched. */
 int rb_register_async(rb_ctx* ctx, size_t first, size_t n);
 
+/* rb_upload + rb_register_async for frames in HOST memory, pipelined: the frames go to the device in
+ * chunks on a second stream and each chunk is registered as soon as it has landed, so the copies of
+ * later frames run under the kernels of earlier ones.  Same results, same fetch calls afterwards.
+ * `frames` must stay valid until the next synchronising call (rb_fetch_*, rb_synchronize); pinned
+ * memory (rb_alloc_host) is what makes the copies overlap. */
+int rb_register_host_async(rb_ctx* ctx, const uint8_t* frames, size_t first, size_t n);
+
 /* Copies the n-1 pair results of the last rb_register_async to the host and waits for them.
  * out[i] belongs to frames (first+i, first+i+1). */
 int rb_fetch_offsets(rb_ctx* ctx, rb_offset* out, size_t n_pairs);
@@ -151,7 +159,7 @@ void rb_free_host(void* p);
 /* Introspection for benchmarks and tests. */
 int rb_synchronize(rb_ctx* ctx);
 void* rb_stream(rb_ctx* ctx);                          /* the cudaStream_t the kernels run on       */
-int rb_kernel_times(rb_ctx* ctx, float* ms, size_t n); /* last rb_register_async: kpe, kpm, declare */
+int rb_kernel_times(rb_ctx* ctx, float* ms, size_t n); /* last rb_register_async: kpe, matcher (all), declare[, lists, match, deferred] */
 uint64_t rb_kernel_launches(rb_ctx* ctx);              /* kernels launched by this context so far   */
 /* (pair, region) ballots of the last rb_register_async that the pipelined matcher deferred to the
  * general kernel (waits for the stream). */

@@ -36,7 +36,7 @@ class Registrar:
 
     def __init__(self, width, height, max_frames, device=0, compute_median=True, profile=False, stream=None,
                  code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3,
-                 kpm_mode=0, list_cap=0, run_pairs=0):
+                 kpm_mode=0, list_cap=0, run_pairs=0, upload_chunk=0):
         self._lib = _lib.load()
         cfg = _lib.RbConfig()
         self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
@@ -47,7 +47,7 @@ class Registrar:
         cfg.profile = int(bool(profile))
         cfg.code_slots, cfg.offset_slots = code_slots, offset_slots
         cfg.stream = stream
-        cfg.kpm_mode, cfg.list_cap, cfg.run_pairs = kpm_mode, list_cap, run_pairs
+        cfg.kpm_mode, cfg.list_cap, cfg.run_pairs, cfg.upload_chunk = kpm_mode, list_cap, run_pairs, upload_chunk
         self.width, self.height, self.max_frames = width, height, max_frames
         self.nreg = grid[0] * grid[1]
         self._ctx = C.c_void_p()
@@ -94,6 +94,13 @@ class Registrar:
 
     def register_async(self, n, first=0):
         self._check(self._lib.rb_register_async(self._ctx, first, n))
+
+    def register_host_async(self, frames, first=0):
+        """upload + register_async for host frames, copies overlapped with the kernels (rb_register_host_async)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width), frames.shape
+        self._check(self._lib.rb_register_host_async(self._ctx, frames.ctypes.data_as(C.c_void_p), first, frames.shape[0]))
+        self._keep = frames
 
     def fetch_offsets(self, n_pairs, out=None):
         if out is None:
@@ -160,9 +167,9 @@ class Registrar:
         return self._lib.rb_stream(self._ctx)
 
     def kernel_times(self):
-        ms = (C.c_float * 3)()
-        self._check(self._lib.rb_kernel_times(self._ctx, ms, 3))
-        return dict(kpe_ms=ms[0], kpm_ms=ms[1], declare_ms=ms[2])
+        ms = (C.c_float * 6)()
+        self._check(self._lib.rb_kernel_times(self._ctx, ms, 6))
+        return dict(kpe_ms=ms[0], kpm_ms=ms[1], declare_ms=ms[2], list_ms=ms[3], match_ms=ms[4], deferred_ms=ms[5])
 
     @property
     def offsets_device_ptr(self):

@@ -144,10 +144,12 @@ __global__ void rb_count_kernel(const uint32_t* __restrict__ bits, size_t nwords
 
 // The general matcher (rb_kpm.cuh) over the (pair, region) list the pipelined matcher deferred.
 __global__ void __launch_bounds__(256) rb_kpm_deferred_kernel(const RbKpmParams p, const uint2* __restrict__ list,
-                                                              const uint32_t* __restrict__ count, uint32_t cap) {
+                                                              const uint32_t* __restrict__ count, uint32_t cap,
+                                                              uint32_t* __restrict__ total) {
   extern __shared__ __align__(16) uint32_t rb_kpm_smem[];
   uint32_t n = *count;
   if (n > cap) n = cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(total, n);  // statistics (rb_deferred_count)
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint2 it = list[i];
     rbm::kpm_block(p, it.x, it.y, rb_kpm_smem, blockDim.x);
@@ -194,7 +196,9 @@ struct rb_ctx {
   size_t kpm_smem;
   size_t uploaded;       // frames [0, uploaded) hold data
   size_t reg_first, reg_n;
-  cudaEvent_t ev[4];
+  cudaEvent_t ev[6];      // profile marks: start, after K1, after K1c, after K2, after deferred/general, end
+  cudaStream_t copy_stream;  // host -> device copies of rb_register_host_async
+  cudaEvent_t ev_copy[2], ev_entry;
   uint64_t launches;
   bool debug_sync;
   std::string err;
@@ -278,7 +282,10 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   RB_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
   if (cfg->stream) { c->stream = static_cast<cudaStream_t>(cfg->stream); c->own_stream = false; }
   else { RB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  for (int i = 0; i < 4; ++i) RB_CUDA(c, cudaEventCreate(&c->ev[i]));
+  for (int i = 0; i < 6; ++i) RB_CUDA(c, cudaEventCreate(&c->ev[i]));
+  RB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
+  RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
 
   // K2 shared-memory budget
   uint32_t maxw = 0, maxh = 0, maxcols = 0;
@@ -414,14 +421,18 @@ void rb_destroy(rb_ctx* c) {
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < 2; ++i)
+    if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+  if (c->ev_entry) cudaEventDestroy(c->ev_entry);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 const char* rb_last_error(rb_ctx* c) { return c ? c->err.c_str() : "null context"; }
-const rb_offset* rb_offsets_device(rb_ctx* c) { return c ? c->d_offsets : nullptr; }
+const rb_offset* rb_offsets_device(rb_ctx* c) { return c ? c->d_offsets + c->reg_first : nullptr; }
 
 int rb_count_keypoints(rb_ctx* c, size_t first, size_t n, uint64_t* total) {
   if (!c || !total) return RB_ERR_INVALID;
@@ -471,26 +482,41 @@ int rb_synchronize(rb_ctx* c) {
   return RB_OK;
 }
 
+// host -> frame store, on `stream`
+static int copy_frames(rb_ctx* c, const uint8_t* frames, size_t first, size_t n, cudaStream_t stream) {
+  const RbGeom& g = c->g;
+  uint8_t* dst = c->d_frames + g.frame_stride * first;
+  if (g.pitch == g.W)
+    RB_CUDA(c, cudaMemcpyAsync(dst, frames, (size_t)g.W * g.H * n, cudaMemcpyHostToDevice, stream));
+  else
+    RB_CUDA(c, cudaMemcpy2DAsync(dst, g.pitch, frames, g.W, g.W, (size_t)g.H * n, cudaMemcpyHostToDevice, stream));
+  return RB_OK;
+}
+
+// K0: the packed 4 bit/pixel copy of frames [first, first + n) that the pipelined matcher reads
+static int pack_frames(rb_ctx* c, size_t first, size_t n) {
+  if (!c->d_frames4 || n == 0) return RB_OK;
+  const RbGeom& g = c->g;
+  const uint64_t chunks = (uint64_t)n * g.H * (g.pitch / 16);
+  uint64_t blocks = (chunks + 255) / 256;
+  const uint64_t maxb = (uint64_t)c->sm_count * 16;
+  if (blocks > maxb) blocks = maxb;
+  rb_pack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(c->d_frames + g.frame_stride * first, g.pitch, g.frame_stride,
+                                                         c->d_frames4 + c->frame_stride4 * first, c->pitch4, c->frame_stride4,
+                                                         g.H, (uint32_t)n);
+  RB_LAUNCHED(c, "rb_pack_kernel");
+  return RB_OK;
+}
+
 int rb_upload(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
   if (!c || !frames) return RB_ERR_INVALID;
   if (first + n > c->cfg.max_frames) { c->err = "rb_upload: beyond max_frames"; return RB_ERR_CAPACITY; }
   if (n == 0) return RB_OK;
-  const RbGeom& g = c->g;
   RB_CUDA(c, cudaSetDevice(c->device));
-  uint8_t* dst = c->d_frames + g.frame_stride * first;
-  if (g.pitch == g.W)
-    RB_CUDA(c, cudaMemcpyAsync(dst, frames, (size_t)g.W * g.H * n, cudaMemcpyHostToDevice, c->stream));
-  else
-    RB_CUDA(c, cudaMemcpy2DAsync(dst, g.pitch, frames, g.W, g.W, (size_t)g.H * n, cudaMemcpyHostToDevice, c->stream));
-  if (c->d_frames4) {  // K0: the packed copy the pipelined matcher reads
-    const uint64_t chunks = (uint64_t)n * g.H * (g.pitch / 16);
-    uint64_t blocks = (chunks + 255) / 256;
-    const uint64_t maxb = (uint64_t)c->sm_count * 16;
-    if (blocks > maxb) blocks = maxb;
-    rb_pack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(dst, g.pitch, g.frame_stride, c->d_frames4 + c->frame_stride4 * first,
-                                                           c->pitch4, c->frame_stride4, g.H, (uint32_t)n);
-    RB_LAUNCHED(c, "rb_pack_kernel");
-  }
+  int rc = copy_frames(c, frames, first, n, c->stream);
+  if (rc != RB_OK) return rc;
+  rc = pack_frames(c, first, n);
+  if (rc != RB_OK) return rc;
   if (first + n > c->uploaded) c->uploaded = first + n;
   return RB_OK;
 }
@@ -512,25 +538,26 @@ static uint32_t pick_segments(const rb_ctx* c, size_t n) {
   return best;
 }
 
-int rb_register_async(rb_ctx* c, size_t first, size_t n) {
-  if (!c) return RB_ERR_INVALID;
-  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register: frame range"; return RB_ERR_CAPACITY; }
-  if (first + n > c->uploaded) { c->err = "rb_register: frames not uploaded"; return RB_ERR_STATE; }
+// Enqueues the registration of frames [first, first + n) on the context's stream: K1 on frames
+// [kpe_first, first + n) (earlier ones were extracted by a previous call), the matcher on the n - 1
+// pairs, K3.  Ballots, results and offsets are stored at the pair's absolute index (= index of its
+// first frame).
+static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
   const RbGeom& g = c->g;
-  RB_CUDA(c, cudaSetDevice(c->device));
   const bool prof = c->cfg.profile != 0;
   if (prof) RB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-  {
+  if (kpe_first < first + n) {
+    const size_t kn = first + n - kpe_first;
     RbKpeParams p;
     p.g = g;
-    p.frames = c->d_frames + g.frame_stride * first;
-    p.median = c->d_median ? c->d_median + g.median_stride * first : nullptr;
-    p.kpbits = c->d_kp + (size_t)first * g.H * g.NS;
-    p.w2bits = c->d_w2 + (size_t)first * g.H * g.NS;
-    p.nframes = (uint32_t)n;
-    p.nseg = pick_segments(c, n);
+    p.frames = c->d_frames + g.frame_stride * kpe_first;
+    p.median = c->d_median ? c->d_median + g.median_stride * kpe_first : nullptr;
+    p.kpbits = c->d_kp + (size_t)kpe_first * g.H * g.NS;
+    p.w2bits = c->d_w2 + (size_t)kpe_first * g.H * g.NS;
+    p.nframes = (uint32_t)kn;
+    p.nseg = pick_segments(c, kn);
     p.seg_rows = (g.H - 6 + p.nseg - 1) / p.nseg;
-    const size_t items = n * p.nseg * g.NS;
+    const size_t items = kn * p.nseg * g.NS;
     const uint32_t blocks = (uint32_t)((items + 127) / 128);
     rb_kpe_kernel<<<blocks, 128, 0, c->stream>>>(p);
     RB_LAUNCHED(c, "rb_kpe_kernel");
@@ -543,50 +570,98 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
     p.frames = c->d_frames;
     p.kpbits = c->d_kp;
     p.w2bits = c->d_w2;
-    p.votes = c->d_votes;
+    p.votes = c->d_votes + first * g.nreg;
     p.first_frame = (uint32_t)first;
     p.npairs = (uint32_t)(n - 1);
     p.code_slots = c->code_slots; p.off_slots = c->off_slots; p.tile_pitch = c->tile_pitch; p.tile_rows = c->tile_rows;
     if (c->cfg.kpm_mode == 0) {
       // K1c: per-(frame, region) keypoint lists; K2: pipelined matcher; then the general kernel over
       // whatever K2 deferred (normally nothing: the grid exits on an empty list)
-      const uint32_t items = (uint32_t)n * g.nreg;
-      uint32_t lblocks = (items + 7) / 8;
-      rb_list_kernel<<<lblocks, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)first, (uint32_t)n, c->fast.lcap, c->d_lists,
-                                                    c->d_counts);
-      RB_LAUNCHED(c, "rb_list_kernel");
-      RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));  // work counter, deferred count, error word
+      if (kpe_first < first + n) {
+        const uint32_t items = (uint32_t)(first + n - kpe_first) * g.nreg;
+        rb_list_kernel<<<(items + 7) / 8, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)kpe_first,
+                                                              (uint32_t)(first + n - kpe_first), c->fast.lcap, c->d_lists,
+                                                              c->d_counts);
+        RB_LAUNCHED(c, "rb_list_kernel");
+      }
+      if (prof) RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+      RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));  // work counter; deferred count / error word accumulate
       RbKpmFastParams f = c->fast;
       f.lists = c->d_lists;
       f.counts = c->d_counts;
-      f.votes = c->d_votes;
+      f.votes = p.votes;
       f.first_frame = (uint32_t)first;
       f.npairs = (uint32_t)(n - 1);
       f.work_counter = c->d_work;
-      f.deferred_count = c->d_work + 1;
+      f.deferred_count = c->d_work + 4;  // per-launch list position; d_work[1] keeps the running total
       f.deferred = c->d_deferred;
       f.deferred_cap = (uint32_t)((n - 1) * g.nreg);
+      RB_CUDA(c, cudaMemsetAsync(c->d_work + 4, 0, 4, c->stream));
       const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
       uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
       if (grid > witems) grid = witems;
       rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
       RB_LAUNCHED(c, "rb_kpm_fast_kernel");
+      if (prof) RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
       uint32_t dgrid = (uint32_t)c->sm_count * 2;
       if (dgrid > f.deferred_cap) dgrid = f.deferred_cap;
-      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, c->d_deferred, c->d_work + 1, f.deferred_cap);
+      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, c->d_deferred, c->d_work + 4, f.deferred_cap, c->d_work + 1);
       RB_LAUNCHED(c, "rb_kpm_deferred_kernel");
     } else {
+      if (prof) { RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream)); }
       rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
       RB_LAUNCHED(c, "rb_kpm_kernel");
     }
-    if (prof) RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, c->d_votes, c->d_results,
-                                                                                   c->d_offsets, (uint32_t)(n - 1));
+    if (prof) RB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, p.votes, c->d_results + first,
+                                                                                   c->d_offsets + first, (uint32_t)(n - 1));
     RB_LAUNCHED(c, "rb_declare_offsets_kernel");
   } else if (prof) {
-    RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    for (int i = 2; i <= 4; ++i) RB_CUDA(c, cudaEventRecord(c->ev[i], c->stream));
   }
-  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+  return RB_OK;
+}
+
+int rb_register_async(rb_ctx* c, size_t first, size_t n) {
+  if (!c) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register: frame range"; return RB_ERR_CAPACITY; }
+  if (first + n > c->uploaded) { c->err = "rb_register: frames not uploaded"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));  // work counter, deferred total, error word
+  const int rc = enqueue_range(c, first, n, first);
+  if (rc != RB_OK) return rc;
+  c->reg_first = first;
+  c->reg_n = n;
+  return RB_OK;
+}
+
+// rb_upload + rb_register_async in one call, with the host -> device copies of later frames running
+// under the kernels of earlier ones: frames go over in chunks on a second stream, and each chunk is
+// registered (with the last frame of the previous chunk as its first `previous`) as soon as it landed.
+int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
+  if (!c || !frames) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const RbGeom& g = c->g;
+  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 2048;
+  // the copies must not overtake earlier work on the main stream that still reads these slots
+  RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
+  RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
+  if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));
+  size_t k = 0;
+  for (size_t at = 0; at < n; at += chunk, ++k) {
+    const size_t m = at + chunk < n ? chunk : n - at;
+    int rc = copy_frames(c, frames + (size_t)g.W * g.H * at, first + at, m, c->copy_stream);
+    if (rc != RB_OK) return rc;
+    RB_CUDA(c, cudaEventRecord(c->ev_copy[k & 1], c->copy_stream));
+    RB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[k & 1], 0));
+    rc = pack_frames(c, first + at, m);
+    if (rc != RB_OK) return rc;
+    if (first + at + m > c->uploaded) c->uploaded = first + at + m;
+    rc = at == 0 ? enqueue_range(c, first, m, first) : enqueue_range(c, first + at - 1, m + 1, first + at);
+    if (rc != RB_OK) return rc;
+  }
   c->reg_first = first;
   c->reg_n = n;
   return RB_OK;
@@ -596,8 +671,11 @@ int rb_kernel_times(rb_ctx* c, float* ms, size_t n) {
   if (!c || !ms || n < 3) return RB_ERR_INVALID;
   if (!c->cfg.profile) { c->err = "context created without profile=1"; return RB_ERR_STATE; }
   RB_CUDA(c, cudaSetDevice(c->device));
-  RB_CUDA(c, cudaEventSynchronize(c->ev[3]));
-  for (int i = 0; i < 3; ++i) RB_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  RB_CUDA(c, cudaEventSynchronize(c->ev[5]));
+  float d[5];
+  for (int i = 0; i < 5; ++i) RB_CUDA(c, cudaEventElapsedTime(&d[i], c->ev[i], c->ev[i + 1]));
+  const float all[6] = {d[0], d[1] + d[2] + d[3], d[4], d[1], d[2], d[3]};  // kpe, matcher total, declare, lists, match, deferred
+  for (size_t i = 0; i < n && i < 6; ++i) ms[i] = all[i];
   return RB_OK;
 }
 
@@ -606,7 +684,7 @@ int rb_fetch_offsets(rb_ctx* c, rb_offset* out, size_t n_pairs) {
   if (c->reg_n == 0 || n_pairs > c->reg_n - 1) { c->err = "rb_fetch_offsets: nothing registered"; return RB_ERR_STATE; }
   RB_CUDA(c, cudaSetDevice(c->device));
   if (n_pairs)
-    RB_CUDA(c, cudaMemcpyAsync(out, c->d_offsets, n_pairs * sizeof(rb_offset), cudaMemcpyDeviceToHost, c->stream));
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_offsets + c->reg_first, n_pairs * sizeof(rb_offset), cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RB_OK;
 }
@@ -662,7 +740,7 @@ int rb_region_ballots(rb_ctx* c, size_t pair, rb_region_vote* out) {
   if (!c || !out) return RB_ERR_INVALID;
   if (c->reg_n < 2 || pair >= c->reg_n - 1) { c->err = "rb_region_ballots: pair not registered"; return RB_ERR_STATE; }
   RB_CUDA(c, cudaSetDevice(c->device));
-  RB_CUDA(c, cudaMemcpyAsync(out, c->d_votes + pair * c->g.nreg, c->g.nreg * sizeof(RbRegionVote),
+  RB_CUDA(c, cudaMemcpyAsync(out, c->d_votes + (c->reg_first + pair) * c->g.nreg, c->g.nreg * sizeof(RbRegionVote),
                              cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RB_OK;

@@ -112,6 +112,26 @@ def test_pipelined_matcher_defers_nothing_on_config2_frames():
         assert reg.deferred_count == 0
 
 
+@pytest.mark.parametrize("chunk", [3, 64, 0])
+def test_pipelined_host_registration_equals_upload_then_register(chunk):
+    """rb_register_host_async (chunked copies overlapped with the kernels, one-frame overlap between
+    chunks) gives the same offsets, ballots and medians as rb_upload + rb_register."""
+    n = 150
+    seq = synth.scrolling_tilemap(n, 320, 224, seed=91, cut_every=35)
+    with remap_b200.Registrar(320, 224, max_frames=n + 5) as reg:
+        reg.upload(seq.frames, first=2)
+        off_a, med_a = reg.register(n, first=2, want_medians=True)
+        ballots_a = np.stack([reg.region_ballots(i) for i in range(n - 1)])
+    with remap_b200.Registrar(320, 224, max_frames=n + 5, upload_chunk=chunk) as reg:
+        reg.register_host_async(seq.frames, first=2)
+        off_b = reg.fetch_offsets(n - 1)
+        med_b = reg.fetch_medians(n, first=2)
+        ballots_b = np.stack([reg.region_ballots(i) for i in range(n - 1)])
+    assert np.array_equal(off_a, off_b) and np.array_equal(med_a, med_b)
+    for fld in ballots_a.dtype.names:
+        assert np.array_equal(ballots_a[fld], ballots_b[fld]), fld
+
+
 def test_dirty_high_nibbles_are_ignored():
     """The reference requires 0..15 (src/cpl.hpp LUT index); the kernels mask to the low nibble."""
     frames = synth.scrolling_tilemap(3, 320, 224, seed=42).frames
