@@ -233,9 +233,10 @@ def main():
 
     def step():
         reg.register_async(n)
-        if world > 1:
+        if world > 1:  # the one exchange of the path: 12 B per pair to rank 0, on the library's stream
             with torch.cuda.stream(stream):
-                gathered["off"] = shard.gather_offsets(dev_off, total_frames)
+                gathered["dev"], gathered["counts"] = shard.gather_offsets_device(dev_off, total_frames,
+                                                                                  out=gathered.get("dev"))
 
     def sync_all():
         if world > 1:
@@ -274,6 +275,13 @@ def main():
     off = reg.fetch_offsets(n - 1)
     ok = bool(((off["flags"] & RB_OFFSET_VALID) != 0).all() and
               np.array_equal(np.stack([off["dx"], off["dy"]], 1), seq.true_offsets))
+    if world > 1:  # every rank checks its own shard; rank 0 reports the conjunction
+        okt = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = bool(okt.item())
+        if rank == 0:  # and the gathered sequence must hold rank 0's pairs at the front
+            g0 = gathered["dev"][0][:n - 1].cpu().numpy()
+            ok = ok and np.array_equal(g0[:, 0], off["dx"]) and np.array_equal(g0[:, 1], off["dy"])
     deferred = reg.deferred_count
     kp_total = reg.count_keypoints(n)
     kpf = kp_total / n

@@ -29,6 +29,29 @@ def shard_range(n_frames: int, world: int, rank: int):
     return first, hi, first, hi - 1
 
 
+def gather_offsets_device(local, n_frames: int, group=None, out=None):
+    """The collective alone, asynchronous on the current stream: gathers every rank's (pairs_r, 3) int32
+    device tensor to rank 0.  Returns (list of per-rank padded tensors on rank 0 | None, counts);
+    `out` lets the caller reuse the receive buffers between steps."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    counts = [s[3] - s[2] for s in (shard_range(n_frames, world, r) for r in range(world))]
+    cap = max(max(counts), 1)
+    assert local.shape[0] == counts[rank], (local.shape, counts[rank])
+    if local.shape[0] == cap:
+        buf = local
+    else:
+        buf = torch.zeros((cap, 3), dtype=torch.int32, device=local.device)
+        buf[:local.shape[0]] = local
+    if rank == 0 and out is None:
+        out = [torch.empty((cap, 3), dtype=torch.int32, device=local.device) for _ in range(world)]
+    dist.gather(buf, out if rank == 0 else None, dst=0, group=group)
+    return (out if rank == 0 else None), counts
+
+
 def gather_offsets(local, n_frames: int, group=None, device=None):
     """Gathers every rank's pair results to rank 0 (one collective per call).
 
@@ -37,25 +60,15 @@ def gather_offsets(local, n_frames: int, group=None, device=None):
     (n_frames - 1,) OFFSET_DTYPE array of the whole sequence, None elsewhere.
     """
     import torch
-    import torch.distributed as dist
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    sizes = [shard_range(n_frames, world, r) for r in range(world)]
-    counts = [s[3] - s[2] for s in sizes]
-    cap = max(max(counts), 1)
     if isinstance(local, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(local).view(np.int32).reshape(-1, 3))
         if device is not None:
             t = t.to(device)
     else:
         t = local
-    assert t.shape[0] == counts[rank], (t.shape, counts[rank])
-    buf = torch.zeros((cap, 3), dtype=torch.int32, device=t.device)
-    buf[:t.shape[0]] = t
-    out = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-    dist.gather(buf, out, dst=0, group=group)
-    if rank != 0:
+    out, counts = gather_offsets_device(t, n_frames, group)
+    if out is None:
         return None
     parts = [o[:c].cpu().numpy() for o, c in zip(out, counts)]
     allp = np.concatenate(parts, 0) if parts else np.zeros((0, 3), np.int32)
