@@ -359,7 +359,8 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->fast_smem = rbf::smem_bytes(f);
     const bool fast_ok = cap >= 16 && bx <= 256 && f.box_y <= 256 && c->fast_smem <= (size_t)smem_max && g.W < 16384 && g.H < 4096 &&
-                         f.offbits <= 24 && f.run <= 1024 && maxcols * maxh < 65536;
+                         f.offbits <= 24 && f.run <= 1024 && maxcols * maxh < 65536 &&
+                         (g.W << dybits) < (1u << 28);
     if (!fast_ok && cfg->kpm_mode == 0) c->cfg.kpm_mode = 1;  // geometry outside the pipelined matcher's limits
     if (c->cfg.kpm_mode == 0) {
       RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fast_smem));

@@ -110,7 +110,7 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 struct Smem {           // stage k of a per-frame array lives at base + k * stride
   uint8_t* tile;        // [2][tile_rows][box_x] packed 4 bit/pixel, + 16 bytes of slack
   uint32_t* plist;      // [2][cap] positions as delivered by the bulk copy
-  uint4* ents;          // [2][cap] (c0, c1, c2, pos | c3 << 28): the frame's codes, kept for its turn as "previous"
+  uint4* ents;          // [2][cap] (c0, c1, c2, x << dybits | y | c3 << 28): the frame's codes, kept for its turn as "previous"
   uint16_t* next;       // [2][cap] chain links: next entry of the same frame in the same bucket, or NIL16
   uint32_t* head;       // [3][tslots] first entry of each bucket's chain, or NIL
   uint32_t* otab;       // [2][oslots] offset id << cntbits | count, or EMPTY
@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
         // the table that will be built next step still holds the chains of two steps ago
         {
           uint4* hc = reinterpret_cast<uint4*>(s.head + tc * p.tslots);
-          for (uint32_t i = tid; i < p.tslots / 4; i += NTP) hc[i] = make_uint4(NIL, NIL, NIL, NIL);
+          const uint32_t nq = p.tslots / 4;
+          if (nq <= NTP) { if (tid < nq) hc[tid] = make_uint4(NIL, NIL, NIL, NIL); }
+          else for (uint32_t i = tid; i < nq; i += NTP) hc[i] = make_uint4(NIL, NIL, NIL, NIL);
         }
         if (st == 0) { mbar_wait(&s.mbar[0], ph0, p.work_counter + 2); ph0 ^= 1; }
         else { mbar_wait(&s.mbar[1], ph1, p.work_counter + 2); ph1 ^= 1; }
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
               if (++probes > MAXPROBE) { s.ctl[2 + st] = 1; break; }  // table (nearly) full: defer
             }
           };
+          const uint32_t obias = (g.W << p.dybits) | g.H;  // (dx + W) << dybits | (dy + H), both fields stay positive
           const uint32_t Lw = (L + 31) & ~31u;  // whole warps iterate together
           for (uint32_t i = tid; i < Lw; i += NTP) {
             uint32_t oid0 = NONE | lane, oid1 = NONE | lane;  // unique per lane: groups of one in match_any
@@ -423,7 +426,10 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
               const uint32_t x = pos & 0x7FFFu, y = pos >> 16;
               const Code c = code_at(tile, wpr, x - 2 - tx0, y - Y0);
               const uint32_t slot = code_hash(c) & tmask;
-              const uint32_t w3 = pos | (c.c3 << 28);  // y < 4096: the top nibble is free for the code's last 4 bits
+              // position as x << dybits | y (< 2^24): prev - curr + bias is then the offset id in one subtraction;
+              // the top nibble carries the code's last 4 bits
+              const uint32_t key = (x << p.dybits) | y;
+              const uint32_t w3 = key | (c.c3 << 28);
               ents[i] = make_uint4(c.c0, c.c1, c.c2, w3);
               next[i] = (uint16_t)atomicExch(&head[slot], i);  // push onto the bucket's chain (NIL -> 0xFFFF)
               if (pair_ok && (use_all || (pos & 0x8000u))) {   // !use_all: weight-2 codes only (src/kpm.hpp:113-117)
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
                   const uint4 pe = pents[j];
                   if (pe.x == c.c0 && pe.y == c.c1 && pe.z == c.c2 && ((pe.w ^ w3) >> 28) == 0) {
                     // equal codes: vote prev - curr (src/kpm.hpp:96-98)
-                    const uint32_t oid = ((((pe.w & 0x7FFFu) - x + g.W) << p.dybits) | (((pe.w >> 16) & 0xFFFu) - y + g.H));
+                    const uint32_t oid = (pe.w & 0x0FFFFFFFu) - key + obias;
                     if (oid0 & NONE) oid0 = oid;
                     else if (oid1 & NONE) oid1 = oid;
                     else vote(oid, 1u);  // third and later matches of one keypoint: rare, one by one

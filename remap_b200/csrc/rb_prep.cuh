@@ -77,14 +77,18 @@ RB_HD void lane_emit(const RbListLane& L, uint32_t ra, uint32_t kw, uint32_t ww,
                      uint32_t cap, uint32_t* out) {
   uint32_t at1 = cap - 1 - n1_before;  // wraps far above cap when the row is full
   const uint32_t yv = ((L.Y0 + ra + L.row0) << 16) + RB_STRIP_OUT * L.j;
-  while (kw) {
-    const uint32_t b = rb_ffs0(kw);
-    kw &= kw - 1;
-    const bool is2 = (ww >> b) & 1u;
-    const uint32_t at = is2 ? at2 : at1;
-    if (at < cap) out[at] = (yv + b) | (is2 ? 0x8000u : 0u);
-    at2 += is2 ? 1u : 0u;
-    at1 -= is2 ? 0u : 1u;
+  uint32_t w2 = ww, w1 = kw & ~ww;  // two short loops beat one loop that selects per bit
+  while (w2) {
+    const uint32_t b = rb_ffs0(w2);
+    w2 &= w2 - 1;
+    if (at2 < cap) out[at2] = (yv + b) | 0x8000u;
+    ++at2;
+  }
+  while (w1) {
+    const uint32_t b = rb_ffs0(w1);
+    w1 &= w1 - 1;
+    if (at1 < cap) out[at1] = yv + b;
+    --at1;
   }
 }
 
