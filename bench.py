@@ -311,8 +311,13 @@ def main():
         if world > 1:
             dist.all_reduce(em, op=dist.ReduceOp.MAX)
         e2e = {"value": total_frames * esteps / float(em.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n * args.width * args.height), "d2h_bytes_per_step": int((n - 1) * 12),
-               "steps": esteps, "note": "rb_register_host_async (pinned host frames, chunked H2D overlapped with the kernels) + "
+               # the library packs the caller's one-byte-per-pixel frames to 4 bit/pixel on host threads before
+               # the copy: these are the bytes that cross PCIe; host_input_bytes is what the caller hands over
+               "h2d_bytes_per_step": int(n * args.height * (((args.width + 1) // 2 + 15) // 16 * 16)),
+               "host_input_bytes_per_step": int(n * args.width * args.height),
+               "d2h_bytes_per_step": int((n - 1) * 12),
+               "steps": esteps, "note": "rb_register_host_async (host frames packed to 4 bpp by host threads, chunked H2D on a copy stream, "
+                                        "both overlapped with the kernels) + "
                                         "rb_fetch_offsets per step; wall clock and CUDA events, the larger of the two, max over ranks"}
 
     if rank == 0:

@@ -17,13 +17,13 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC,-mavx2,-fopenmp", "-shared",
     "-Xptxas", "-v",
 ]
 
 
 def sources():
-    return [os.path.join(CSRC, "rb_api.cu")]
+    return [os.path.join(CSRC, "rb_api.cu"), os.path.join(CSRC, "rb_hostpack.cpp")]
 
 
 def deps():
@@ -37,7 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(d) for d in deps()):
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + sources() + ["-o", LIB]
+    cmd = [nvcc] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC] + sources() + ["-o", LIB, "-lgomp"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

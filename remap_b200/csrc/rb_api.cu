@@ -12,6 +12,7 @@
 
 #include "../../include/remap_b200.h"
 #include "rb_host.hpp"
+#include "rb_hostpack.hpp"
 #include "rb_kpe.cuh"
 #include "rb_kpm.cuh"
 #include "rb_kpm_fast.cuh"
@@ -199,6 +200,8 @@ struct rb_ctx {
   cudaEvent_t ev[6];      // profile marks: start, after K1, after K1c, after K2, after deferred/general, end
   cudaStream_t copy_stream;  // host -> device copies of rb_register_host_async
   cudaEvent_t ev_copy[2], ev_entry;
+  uint8_t* h_stage[2];     // pinned staging: two chunks of packed 4 bit/pixel frames
+  size_t stage_frames;
   uint64_t launches;
   bool debug_sync;
   std::string err;
@@ -427,6 +430,8 @@ void rb_destroy(rb_ctx* c) {
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
   if (c->ev_entry) cudaEventDestroy(c->ev_entry);
+  for (int i = 0; i < 2; ++i)
+    if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -637,15 +642,23 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
   return RB_OK;
 }
 
-// rb_upload + rb_register_async in one call, with the host -> device copies of later frames running
-// under the kernels of earlier ones: frames go over in chunks on a second stream, and each chunk is
-// registered (with the last frame of the previous chunk as its first `previous`) as soon as it landed.
+// rb_upload + rb_register_async in one call, pipelined three deep: host threads pack chunk k + 1 to
+// 4 bit/pixel in pinned staging (half the bytes cross PCIe) while chunk k is on the bus (second stream)
+// and chunk k - 1 is being registered (with the last frame of its predecessor as its first `previous`).
 int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
   if (!c || !frames) return RB_ERR_INVALID;
   if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
   RB_CUDA(c, cudaSetDevice(c->device));
   const RbGeom& g = c->g;
-  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 2048;
+  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 1024;
+  const bool packed = c->d_frames4 != nullptr;  // the 4 bit/pixel store exists: ship frames packed
+  if (packed && c->stage_frames < chunk) {
+    for (int i = 0; i < 2; ++i) {
+      if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
+      RB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage[i]), c->frame_stride4 * chunk, cudaHostAllocDefault));
+    }
+    c->stage_frames = chunk;
+  }
   // the copies must not overtake earlier work on the main stream that still reads these slots
   RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
   RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
@@ -653,12 +666,28 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   size_t k = 0;
   for (size_t at = 0; at < n; at += chunk, ++k) {
     const size_t m = at + chunk < n ? chunk : n - at;
-    int rc = copy_frames(c, frames + (size_t)g.W * g.H * at, first + at, m, c->copy_stream);
-    if (rc != RB_OK) return rc;
+    int rc;
+    if (packed) {
+      if (k >= 2) RB_CUDA(c, cudaEventSynchronize(c->ev_copy[k & 1]));  // staging buffer k & 1 is free again
+      rb_hostpack_frames(frames + (size_t)g.W * g.H * at, g.W, g.H, m, c->h_stage[k & 1], c->pitch4);
+      RB_CUDA(c, cudaMemcpyAsync(c->d_frames4 + c->frame_stride4 * (first + at), c->h_stage[k & 1], c->frame_stride4 * m,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+    } else {
+      rc = copy_frames(c, frames + (size_t)g.W * g.H * at, first + at, m, c->copy_stream);
+      if (rc != RB_OK) return rc;
+    }
     RB_CUDA(c, cudaEventRecord(c->ev_copy[k & 1], c->copy_stream));
     RB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[k & 1], 0));
-    rc = pack_frames(c, first + at, m);
-    if (rc != RB_OK) return rc;
+    if (packed) {  // K0u: the one-colour-per-byte store K1 reads
+      const uint64_t chunks16 = (uint64_t)m * g.H * (g.pitch / 16);
+      uint64_t blocks = (chunks16 + 255) / 256;
+      const uint64_t maxb = (uint64_t)c->sm_count * 16;
+      if (blocks > maxb) blocks = maxb;
+      rb_unpack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(c->d_frames4 + c->frame_stride4 * (first + at), c->pitch4,
+                                                               c->frame_stride4, c->d_frames + g.frame_stride * (first + at),
+                                                               g.pitch, g.frame_stride, g.H, (uint32_t)m);
+      RB_LAUNCHED(c, "rb_unpack_kernel");
+    }
     if (first + at + m > c->uploaded) c->uploaded = first + at + m;
     rc = at == 0 ? enqueue_range(c, first, m, first) : enqueue_range(c, first + at - 1, m + 1, first + at);
     if (rc != RB_OK) return rc;

@@ -1,0 +1,51 @@
+// rb_hostpack.cpp -- host side of rb_register_host_async: frames as the caller holds them (one
+// colour per byte, src/nil.hpp:14-31) -> the packed 4 bit/pixel rows of the device frame store,
+// written into pinned staging memory.  This is data marshalling for the PCIe copy (half the bytes
+// cross the bus), not a compute path: nothing of kpe / kpm runs on the host.
+#include "rb_hostpack.hpp"
+
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__AVX2__)
+#include <immintrin.h>
+#endif
+
+// one row: W pixels (bytes, low nibble significant) -> pitch4 bytes, pixel x in nibble x & 1 of byte x >> 1
+static inline void pack_row(const uint8_t* src, uint32_t W, uint8_t* dst, uint32_t pitch4) {
+  uint32_t x = 0;
+#if defined(__AVX2__)
+  const __m256i lo = _mm256_set1_epi8(0x0F), w = _mm256_set1_epi16(0x1001);
+  // 64 pixels -> one 32-byte non-temporal store: the staging buffer is written once and read by the DMA
+  // engine only, so it should not be pulled into the cache first
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0)
+    for (; x + 64 <= W; x += 64) {
+      __m256i a = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + x)), lo);
+      __m256i b = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + x + 32)), lo);
+      a = _mm256_maddubs_epi16(a, w);
+      b = _mm256_maddubs_epi16(b, w);
+      __m256i v = _mm256_packus_epi16(a, b);               // per 128-bit half: a.half, b.half
+      v = _mm256_permute4x64_epi64(v, 0xD8);               // a.lo a.hi b.lo b.hi
+      _mm256_stream_si256(reinterpret_cast<__m256i*>(dst + x / 2), v);
+    }
+  for (; x + 32 <= W; x += 32) {
+    __m256i v = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + x)), lo);
+    v = _mm256_maddubs_epi16(v, w);                       // 16-bit lanes: even pixel + 16 * odd pixel
+    v = _mm256_packus_epi16(v, _mm256_setzero_si256());   // bytes, per 128-bit half
+    v = _mm256_permute4x64_epi64(v, 0x08);                // halves' low quadwords side by side
+    _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + x / 2), _mm256_castsi256_si128(v));
+  }
+#endif
+  for (; x + 2 <= W; x += 2) dst[x / 2] = (uint8_t)((src[x] & 15) | ((src[x + 1] & 15) << 4));
+  if (x < W) { dst[x / 2] = (uint8_t)(src[x] & 15); x += 2; }
+  if (x / 2 < pitch4) memset(dst + x / 2, 0, pitch4 - x / 2);
+}
+
+void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4) {
+  const long long rows = (long long)n * H;
+#pragma omp parallel for schedule(static)
+  for (long long r = 0; r < rows; ++r) pack_row(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+#if defined(__AVX2__)
+  _mm_sfence();  // the streaming stores must be visible before the copy is queued
+#endif
+}

@@ -1,0 +1,8 @@
+// rb_hostpack.hpp -- see rb_hostpack.cpp
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+// frames: n * H rows of W bytes (dense) -> dst: n * H rows of pitch4 bytes, 4 bit/pixel.  Multi-threaded.
+// C linkage only so that the CPU test-suite can reach it through ctypes; not part of the public ABI.
+extern "C" void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4);

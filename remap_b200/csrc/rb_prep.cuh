@@ -118,6 +118,30 @@ __global__ void __launch_bounds__(256) rb_pack_kernel(const uint8_t* __restrict_
   }
 }
 
+// K0u: the inverse of rb_pack_kernel, for frames that crossed PCIe already packed
+// (rb_register_host_async): 16 pixels per thread, one 64-bit load, one 128-bit store.
+__global__ void __launch_bounds__(256) rb_unpack_kernel(const uint8_t* __restrict__ src, uint32_t pitch4, uint64_t frame_stride4,
+                                                        uint8_t* __restrict__ dst, uint32_t pitch, uint64_t frame_stride,
+                                                        uint32_t H, uint32_t nframes) {
+  const uint32_t cpr = pitch / 16;  // chunks per row
+  const uint64_t total = (uint64_t)nframes * H * cpr;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t c = (uint32_t)(i % cpr);
+    const uint64_t fy = i / cpr;
+    const uint32_t y = (uint32_t)(fy % H);
+    const uint64_t f = fy / H;
+    uint2 v = make_uint2(0, 0);
+    if (8 * c + 8 <= pitch4) v = __ldg(reinterpret_cast<const uint2*>(src + f * frame_stride4 + (uint64_t)y * pitch4 + 8 * c));
+    auto spread = [](uint32_t h) {  // 4 nibbles (16 bits) -> 4 bytes
+      uint32_t r = (h | (h << 8)) & 0x00FF00FFu;
+      return (r | (r << 4)) & 0x0F0F0F0Fu;
+    };
+    uint4 o;
+    o.x = spread(v.x & 0xFFFFu); o.y = spread(v.x >> 16); o.z = spread(v.y & 0xFFFFu); o.w = spread(v.y >> 16);
+    *reinterpret_cast<uint4*>(dst + f * frame_stride + (uint64_t)y * pitch + 16 * c) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint32_t* __restrict__ kpbits,
                                                       const uint32_t* __restrict__ w2bits, uint32_t first_frame,
                                                       uint32_t nframes, uint32_t cap, uint32_t* __restrict__ lists,

@@ -54,3 +54,23 @@ def test_product_never_touches_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert not re.search(r"#\s*include[^\n]*oracle", text), f
                 assert "libremap_oracle" not in text and "_ref/ref_harness" not in text, f
+
+
+def test_host_side_nibble_packing_for_the_pcie_copy():
+    """rb_register_host_async ships frames as 4 bit/pixel: the host packer (rb_hostpack.cpp, AVX2 + scalar
+    tail, multi-threaded) against numpy, including odd widths, padding and dirty high nibbles."""
+    lib = _lib.load()
+    fn = lib.rb_hostpack_frames
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_uint32]
+    rng = np.random.default_rng(5)
+    for W, H, n in ((320, 224, 3), (323, 227, 2), (33, 9, 5), (8, 8, 1), (1, 4, 2)):
+        frames = rng.integers(0, 256, size=(n, H, W), dtype=np.uint8)
+        pitch4 = ((W + 1) // 2 + 15) // 16 * 16
+        out = np.full((n, H, pitch4), 0xAB, np.uint8)
+        fn(frames.ctypes.data_as(C.c_void_p), W, H, n, out.ctypes.data_as(C.c_void_p), pitch4)
+        lo = frames & 15
+        padded = np.zeros((n, H, 2 * pitch4), np.uint8)
+        padded[:, :, :W] = lo
+        want = padded[:, :, 0::2] | (padded[:, :, 1::2] << 4)
+        assert np.array_equal(out, want), (W, H)

@@ -112,18 +112,19 @@ def test_pipelined_matcher_defers_nothing_on_config2_frames():
         assert reg.deferred_count == 0
 
 
-@pytest.mark.parametrize("chunk", [3, 64, 0])
-def test_pipelined_host_registration_equals_upload_then_register(chunk):
+@pytest.mark.parametrize("chunk,size", [(3, (320, 224)), (64, (320, 224)), (0, (320, 224)), (17, (323, 227)), (40, (200, 136))])
+def test_pipelined_host_registration_equals_upload_then_register(chunk, size):
     """rb_register_host_async (chunked copies overlapped with the kernels, one-frame overlap between
     chunks) gives the same offsets, ballots and medians as rb_upload + rb_register."""
     n = 150
-    seq = synth.scrolling_tilemap(n, 320, 224, seed=91, cut_every=35)
-    with remap_b200.Registrar(320, 224, max_frames=n + 5) as reg:
+    W, H = size
+    seq = synth.scrolling_tilemap(n, W, H, seed=91, cut_every=35)
+    with remap_b200.Registrar(W, H, max_frames=n + 5) as reg:
         reg.upload(seq.frames, first=2)
         off_a, med_a = reg.register(n, first=2, want_medians=True)
         ballots_a = np.stack([reg.region_ballots(i) for i in range(n - 1)])
-    with remap_b200.Registrar(320, 224, max_frames=n + 5, upload_chunk=chunk) as reg:
-        reg.register_host_async(seq.frames, first=2)
+    with remap_b200.Registrar(W, H, max_frames=n + 5, upload_chunk=chunk) as reg:
+        reg.register_host_async(seq.frames | 0x50, first=2)  # dirty high nibbles must not matter
         off_b = reg.fetch_offsets(n - 1)
         med_b = reg.fetch_medians(n, first=2)
         ballots_b = np.stack([reg.region_ballots(i) for i in range(n - 1)])
