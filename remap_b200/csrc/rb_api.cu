@@ -173,7 +173,10 @@ struct rb_ctx {
   uint64_t frame_stride4;
   uint32_t* d_lists;     // [frame][region][list_cap] keypoint positions (K1c)
   uint2* d_counts;       // [frame][region] (n_all, n_w2)
-  uint2* d_deferred;     // [pair][region] worst case
+  uint2* d_deferred;     // [pair][region] worst case: what the first matcher pass deferred
+  uint2* d_deferred2;    // ... and what the second, large-list pass deferred (general kernel)
+  RbKpmFastParams fast2; // second pass: one CTA per SM, lists up to ~2,000 entries, one pair per work item
+  size_t fast2_smem;
   uint32_t* d_work;      // [0] work-item counter, [1] deferred count
   CUtensorMap tmap;      // 3-D tensor map of d_frames4: (row bytes, rows, frames)
   RbKpmFastParams fast;  // geometry-dependent constants of the pipelined matcher
@@ -349,13 +352,13 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     f.dybits = dybits;
     f.offbits = dxbits + dybits;
     const uint32_t cntmax = f.offbits < 32 ? (1u << (32 - f.offbits)) - 1u : 0u;
-    uint32_t cap = cfg->list_cap ? cfg->list_cap : 1024;
+    uint32_t cap = cfg->list_cap ? cfg->list_cap : 1280;
     if (cap > 2047) cap = 2047;
     if (cap > cntmax) cap = cntmax;  // a bin's count never exceeds the shorter list
     cap &= ~3u;                      // 16-byte list rows
     f.cap = cap;
     f.lcap = 2 * cap;  // list rows hold all keypoints of a region even when only the weight-2 ones take part
-    f.tslots = next_pow2(2 * cap < 64 ? 64 : 2 * cap);
+    f.tslots = next_pow2(cap < 2048 ? (cap < 64 ? 64 : (cap > 1024 ? 2048 : 2 * cap)) : cap);  // chained buckets: load <= 1 is fine
     f.oslots = 1024;
     f.run = cfg->run_pairs ? cfg->run_pairs : 32;
     int smem_max = 0;
@@ -374,6 +377,20 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
       RB_CUDA(c, dmalloc(c, &c->d_lists, (size_t)N * g.nreg * f.lcap * 4 + 256));
       RB_CUDA(c, dmalloc(c, &c->d_counts, (size_t)N * g.nreg * sizeof(uint2)));
       RB_CUDA(c, dmalloc(c, &c->d_deferred, (size_t)N * g.nreg * sizeof(uint2)));
+      RB_CUDA(c, dmalloc(c, &c->d_deferred2, (size_t)N * g.nreg * sizeof(uint2)));
+      // second pass for regions whose lists do not fit the first: the same kernel with the largest lists
+      // one CTA can hold (capped by the list rows, the 11-bit entry index and the bin count field)
+      c->fast2 = f;
+      uint32_t cap2 = f.lcap < 2044 ? f.lcap : 2044;
+      if (cap2 > cntmax) cap2 = cntmax;
+      cap2 &= ~3u;
+      c->fast2.cap = cap2;
+      c->fast2.tslots = next_pow2(cap2 < 64 ? 64 : cap2);
+      c->fast2.oslots = 2048;
+      c->fast2_smem = rbf::smem_bytes(c->fast2);
+      if (cap2 <= cap || c->fast2_smem > (size_t)smem_max) c->fast2_smem = 0;  // no second pass
+      RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(c->fast2_smem > c->fast_smem ? c->fast2_smem : c->fast_smem)));
       RB_CUDA(c, dmalloc(c, &c->d_work, 256));
       RB_CUDA(c, cudaMemsetAsync(c->d_frames4, 0, c->frame_stride4 * N + 256, c->stream));
       RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 256, c->stream));
@@ -421,7 +438,7 @@ void rb_destroy(rb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_frames4); cudaFree(c->d_lists); cudaFree(c->d_counts); cudaFree(c->d_deferred); cudaFree(c->d_work);
+  cudaFree(c->d_frames4); cudaFree(c->d_lists); cudaFree(c->d_counts); cudaFree(c->d_deferred); cudaFree(c->d_deferred2); cudaFree(c->d_work);
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
@@ -602,6 +619,7 @@ static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
       f.deferred_count = c->d_work + 4;  // per-launch list position; d_work[1] keeps the running total
       f.deferred = c->d_deferred;
       f.deferred_cap = (uint32_t)((n - 1) * g.nreg);
+      f.items = nullptr; f.nitems = nullptr;
       RB_CUDA(c, cudaMemsetAsync(c->d_work + 4, 0, 4, c->stream));
       const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
       uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
@@ -609,9 +627,29 @@ static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
       rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
       RB_LAUNCHED(c, "rb_kpm_fast_kernel");
       if (prof) RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+      const uint2* glist = c->d_deferred;
+      const uint32_t* gcount = c->d_work + 4;
+      if (c->fast2_smem) {  // second pass over what the first deferred (exits at once on an empty list)
+        RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));
+        RB_CUDA(c, cudaMemsetAsync(c->d_work + 5, 0, 4, c->stream));
+        RbKpmFastParams f2 = c->fast2;
+        f2.lists = c->d_lists; f2.counts = c->d_counts; f2.votes = p.votes;
+        f2.first_frame = (uint32_t)first; f2.npairs = (uint32_t)(n - 1);
+        f2.items = c->d_deferred; f2.nitems = c->d_work + 4;
+        f2.work_counter = c->d_work;
+        f2.deferred_count = c->d_work + 5;
+        f2.deferred = c->d_deferred2;
+        f2.deferred_cap = f.deferred_cap;
+        uint32_t grid2 = (uint32_t)c->sm_count;
+        if (grid2 > f.deferred_cap) grid2 = f.deferred_cap;
+        rb_kpm_fast_kernel<<<grid2, RB_FAST_NT, c->fast2_smem, c->stream>>>(c->tmap, f2);
+        RB_LAUNCHED(c, "rb_kpm_fast_kernel (second pass)");
+        glist = c->d_deferred2;
+        gcount = c->d_work + 5;
+      }
       uint32_t dgrid = (uint32_t)c->sm_count * 2;
       if (dgrid > f.deferred_cap) dgrid = f.deferred_cap;
-      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, c->d_deferred, c->d_work + 4, f.deferred_cap, c->d_work + 1);
+      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, glist, gcount, f.deferred_cap, c->d_work + 1);
       RB_LAUNCHED(c, "rb_kpm_deferred_kernel");
     } else {
       if (prof) { RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream)); }

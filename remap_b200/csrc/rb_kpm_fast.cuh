@@ -54,6 +54,8 @@ struct RbKpmFastParams {
   uint32_t box_x, box_y;   // TMA box: bytes per tile row, rows per box
   uint32_t nbox_y;         // boxes stacked vertically per tile (tile rows = nbox_y * box_y)
   uint32_t dybits, offbits;  // offset id = (dx + W) << dybits | (dy + H), offbits bits in all
+  const uint2* items;      // nullptr: work item i = (region i % nreg, run i / nreg).  Otherwise a second pass
+  const uint32_t* nitems;  //   over (pair, region) entries another launch deferred: item i = items[i], one pair each
   uint32_t* work_counter;  // [0] work items, [2] error word; zeroed before launch
   uint32_t* deferred_count;
   uint2* deferred;         // (pair, region)
@@ -227,7 +229,8 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
   constexpr uint32_t NT = RB_FAST_NT, NTP = RB_FAST_NTP;
   const bool ballot_warp = tid >= NTP;
   const uint32_t runs = (p.npairs + p.run - 1) / p.run;
-  const uint32_t nitems = runs * g.nreg;
+  uint32_t nitems = runs * g.nreg;
+  if (p.items) { nitems = *p.nitems; if (nitems > p.deferred_cap) nitems = p.deferred_cap; }
 
   // ---- one-off set-up: barriers, clean tables -------------------------------------------------
   if (tid == 0) {
@@ -321,9 +324,9 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
     const uint32_t item = s.ctl[4];
     if (item >= nitems) break;
     // regions vary fastest so that the CTAs running at the same time share frames in L2
-    const uint32_t region = item % g.nreg, runidx = item / g.nreg;
-    const uint32_t pa = runidx * p.run;
-    const uint32_t pb = pa + p.run < p.npairs ? pa + p.run : p.npairs;  // pairs [pa, pb)
+    uint32_t region = item % g.nreg, pa = (item / g.nreg) * p.run;
+    uint32_t pb = pa + p.run < p.npairs ? pa + p.run : p.npairs;  // pairs [pa, pb)
+    if (p.items) { const uint2 it = p.items[item]; pa = it.x; pb = pa + 1; region = it.y; }
     const uint32_t fa = p.first_frame + pa;                             // frames fa .. fa + nsteps - 1
     const uint32_t nsteps = pb - pa + 1;
     const uint32_t cs = region / g.grid_h, rs = region % g.grid_h;     // idx = grid_h*col + row (src/kpr.hpp:71-74)

@@ -1,0 +1,114 @@
+"""-m gpu: BASELINE.json configs 3, 4 and 5 at sizes one GPU handles in seconds: a sampled diff against
+the oracle, the sequence-level properties, and the measured throughput (written to
+gpurun_out/configs.json so that profiles/ can quote it; the bench line itself stays config 2)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gpu_common
+import remap_b200
+from oracle import oracle
+from remap_b200 import RB_OFFSET_TIE_SENSITIVE, RB_OFFSET_VALID, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _record(name, **kw):
+    path = os.path.join(ROOT, "gpurun_out", "configs.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = kw
+    json.dump(data, open(path, "w"), indent=1)
+
+
+def _sampled_oracle_diff(reg, frames, offsets, pairs, W, H):
+    """medians, keypoints and declared offsets of the sampled pairs against the C restatement"""
+    cfg = oracle.config(W, H)
+    flagged = 0
+    for i in pairs:
+        i = int(i)
+        _, kp_a = oracle.extract(cfg, frames[i])
+        med_b, kp_b = oracle.extract(cfg, frames[i + 1])
+        assert np.array_equal(reg.fetch_medians(1, first=i + 1)[0], med_b), f"median of frame {i + 1}"
+        kps = reg.keypoints(i + 1)
+        assert np.array_equal(kps["x"], kp_b["x"]) and np.array_equal(kps["y"], kp_b["y"])
+        assert np.array_equal(kps["code"], kp_b["code"]) and np.array_equal(kps["region_mask"], kp_b["region_mask"])
+        ores, ovotes = oracle.match(cfg, kp_a, kp_b)
+        ballots = reg.region_ballots(i)
+        for fld in ballots.dtype.names:
+            assert np.array_equal(ballots[fld], ovotes[fld]), f"pair {i}: ballot field {fld}"
+        rec = gpu_common.result_record(offsets[i], ballots)
+        assert rec["valid"] == bool(ores["valid"]) and (rec["dx"], rec["dy"]) == (int(ores["dx"]), int(ores["dy"]))
+        assert rec["tie_sensitive"] == bool(ores["tie_sensitive"])
+        flagged += rec["tie_sensitive"]
+    return flagged
+
+
+def _timed_register(reg, n, reps=3):
+    best = None
+    for _ in range(reps):
+        reg.register_async(n)
+        t = reg.kernel_times()
+        tot = t["kpe_ms"] + t["kpm_ms"] + t["declare_ms"]
+        if best is None or tot < best[0]:
+            best = (tot, t)
+    return best
+
+
+def test_config3_sprites_and_foreground_mask():
+    """320x224 tilemap with moving sprites; also runs generate_mask against the true background."""
+    n, W, H = 12500, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=3, sprites=12)
+    with remap_b200.Registrar(W, H, max_frames=n, profile=True) as reg:
+        reg.upload(seq.frames)
+        tot, t = _timed_register(reg, n)
+        off = reg.fetch_offsets(n - 1)
+        valid = (off["flags"] & RB_OFFSET_VALID) != 0
+        # sprites are a small part of the picture: the camera motion must still win almost everywhere
+        agree = valid & (off["dx"] == seq.true_offsets[:, 0]) & (off["dy"] == seq.true_offsets[:, 1])
+        assert agree.mean() > 0.99, agree.mean()
+        rng = np.random.default_rng(3)
+        flagged = _sampled_oracle_diff(reg, seq.frames, off, rng.integers(0, n - 1, size=10), W, H)
+        kpf = reg.count_keypoints(n) / n
+        _record("config3_sprites", frames=n, ms=tot, frames_per_s=n / tot * 1e3, kernel_ms=t, keypoints_per_frame=kpf,
+                deferred_ballots=reg.deferred_count, flagged_in_sample=int(flagged), agree_with_camera=float(agree.mean()))
+
+
+def test_config4_640x480_dense():
+    """640x480, scroll up to +-48 px/frame, 10 % speckle (~20 k keypoints/frame)."""
+    n, W, H = 2000, 640, 480
+    seq = synth.scrolling_tilemap(n, W, H, seed=4, speckle=0.10, vmax=(48, 48))
+    with remap_b200.Registrar(W, H, max_frames=n, profile=True) as reg:
+        reg.upload(seq.frames)
+        tot, t = _timed_register(reg, n)
+        off = reg.fetch_offsets(n - 1)
+        assert ((off["flags"] & RB_OFFSET_VALID) != 0).all()
+        assert np.array_equal(np.stack([off["dx"], off["dy"]], 1), seq.true_offsets)
+        rng = np.random.default_rng(4)
+        flagged = _sampled_oracle_diff(reg, seq.frames, off, rng.integers(0, n - 1, size=4), W, H)
+        kpf = reg.count_keypoints(n) / n
+        _record("config4_640x480", frames=n, ms=tot, frames_per_s=n / tot * 1e3, kernel_ms=t, keypoints_per_frame=kpf,
+                deferred_ballots=reg.deferred_count, flagged_in_sample=int(flagged))
+
+
+def test_config5_levels_cuts_parallax():
+    """three levels with hard cuts and a second layer at half speed (32-px bands)."""
+    n, W, H = 12000, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=5, cut_every=3000, levels=3, parallax=32)
+    with remap_b200.Registrar(W, H, max_frames=n, profile=True) as reg:
+        reg.upload(seq.frames)
+        tot, t = _timed_register(reg, n)
+        off = reg.fetch_offsets(n - 1)
+        valid = (off["flags"] & RB_OFFSET_VALID) != 0
+        cuts = np.nonzero(seq.level[1:] != seq.level[:-1])[0]
+        assert len(cuts) >= 2 and not valid[cuts].any(), "a scene cut must not declare an offset"
+        rng = np.random.default_rng(5)
+        sample = np.concatenate([rng.integers(0, n - 1, size=8), cuts[:2]])
+        flagged = _sampled_oracle_diff(reg, seq.frames, off, sample, W, H)
+        kpf = reg.count_keypoints(n) / n
+        _record("config5_cuts_parallax", frames=n, ms=tot, frames_per_s=n / tot * 1e3, kernel_ms=t, keypoints_per_frame=kpf,
+                deferred_ballots=reg.deferred_count, flagged_in_sample=int(flagged), valid_fraction=float(valid.mean()),
+                tie_sensitive_fraction=float(((off["flags"] & RB_OFFSET_TIE_SENSITIVE) != 0).mean()))
