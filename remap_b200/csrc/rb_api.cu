@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <new>
 #include <string>
@@ -275,6 +276,10 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   c->cfg = *cfg;
   c->device = cfg->device;
   c->debug_sync = getenv("RB_DEBUG_SYNC") != nullptr;
+  {  // host packer threads: this process's fair share of the host when there is one process per GPU
+    const long procs = sysconf(_SC_NPROCESSORS_ONLN);
+    rb_hostpack_set_threads((int)(procs > 0 ? (procs / ndev > 0 ? procs / ndev : 1) : 1));
+  }
   *out = c;  // returned even on failure so that rb_last_error can be read; caller rb_destroy()s it
   if (cfg->max_frames < 2) { c->err = "max_frames must be >= 2"; return RB_ERR_INVALID; }
   if (rb_make_geom(cfg->width, cfg->height, cfg->grid_w, cfg->grid_h, cfg->overlap, cfg->weight_switch,

@@ -4,7 +4,9 @@
 // cross the bus), not a compute path: nothing of kpe / kpm runs on the host.
 #include "rb_hostpack.hpp"
 
+#include <omp.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #if defined(__AVX2__)
@@ -41,9 +43,16 @@ static inline void pack_row(const uint8_t* src, uint32_t W, uint8_t* dst, uint32
   if (x / 2 < pitch4) memset(dst + x / 2, 0, pitch4 - x / 2);
 }
 
+static int g_threads = 0;
+void rb_hostpack_set_threads(int threads) { g_threads = threads; }
+
 void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4) {
   const long long rows = (long long)n * H;
-#pragma omp parallel for schedule(static)
+  // an explicit count: launchers such as torchrun export OMP_NUM_THREADS=1, which would serialise the packer
+  int nt = g_threads > 0 ? g_threads : omp_get_num_procs();
+  if (const char* e = getenv("RB_HOST_THREADS")) { const int v = atoi(e); if (v > 0) nt = v; }
+  if (nt < 1) nt = 1;
+#pragma omp parallel for schedule(static) num_threads(nt)
   for (long long r = 0; r < rows; ++r) pack_row(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
 #if defined(__AVX2__)
   _mm_sfence();  // the streaming stores must be visible before the copy is queued

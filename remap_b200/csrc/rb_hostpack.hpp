@@ -6,3 +6,7 @@
 // frames: n * H rows of W bytes (dense) -> dst: n * H rows of pitch4 bytes, 4 bit/pixel.  Multi-threaded.
 // C linkage only so that the CPU test-suite can reach it through ctypes; not part of the public ABI.
 extern "C" void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4);
+
+// Host threads the packer uses (default: all processors).  The context sets processors / visible GPUs,
+// so that one process per GPU shares the host fairly; RB_HOST_THREADS in the environment overrides both.
+extern "C" void rb_hostpack_set_threads(int threads);
