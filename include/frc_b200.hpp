@@ -25,6 +25,8 @@
 #include "ifd.hpp"
 #include "kpr.hpp"
 
+#include <algorithm>
+#include <cstdint>
 #include <cstring>
 #include <list>
 #include <stdexcept>
@@ -50,6 +52,12 @@ struct options {
   std::size_t batch{2048};  // frames registered per rb_register call
   int device{0};
   bool fill_keys{false};    // rebuild the kpr::grid for the callback from rb_keypoints
+  // Map assembly on the GPU (rb_blit_blend) instead of fgm::fragment::blit per frame on the host.  All
+  // frames then stay resident in the device frame store, so the sequence must fit `max_frames`; a
+  // fragment's dots are filled when the fragment ends (next fragment opens, or complete()), i.e. the
+  // fragment handed to the callback has its frames but not yet its dots.
+  bool gpu_blit{false};
+  std::size_t max_frames{0};  // capacity of the frame store with gpu_blit
 };
 
 class collector {
@@ -67,7 +75,8 @@ public:
     rb_default_config(&cfg,
                       static_cast<std::uint32_t>(dimensions.width_),
                       static_cast<std::uint32_t>(dimensions.height_),
-                      static_cast<std::uint32_t>(opt_.batch + 1));
+                      static_cast<std::uint32_t>(opt_.gpu_blit ? std::max(opt_.max_frames, opt_.batch + 1)
+                                                               : opt_.batch + 1));
     cfg.grid_w = grid_horizontal;
     cfg.grid_h = grid_vertical;
     cfg.overlap = grid_overlap;
@@ -123,18 +132,24 @@ public:
       }
 
       // slot 0 of the device frame store = last frame of the previous batch (the `previous` grid
-      // of src/frc.hpp:64-65); slots 1.. = this batch
+      // of src/frc.hpp:64-65); slots 1.. = this batch.  With gpu_blit every frame keeps its own slot
+      // (its index in the sequence) and the previous frame is simply still there.
       auto base{first_batch ? std::size_t{0} : std::size_t{1}};
-      if (!first_batch) {
+      if (!first_batch && !opt_.gpu_blit) {
         std::memcpy(stage_, carry_.data(), pixels);
       }
+      auto skip{opt_.gpu_blit ? base : std::size_t{0}};  // staged frames that need no upload
       for (std::size_t i{0}; i < frames.size(); ++i) {
         std::memcpy(stage_ + (base + i) * pixels, frames[i].image_.data(), pixels);
       }
 
       auto total{base + frames.size()};
-      check(rb_upload(ctx_, stage_, 0, total));
-      check(rb_register(ctx_, 0, total, offsets_, medians_));
+      auto slot0{opt_.gpu_blit ? count_ - base : std::size_t{0}};  // store slot of staged frame 0
+      if (opt_.gpu_blit && count_ + frames.size() > std::max(opt_.max_frames, opt_.batch + 1)) {
+        throw std::runtime_error("frc_b200::collector: sequence longer than options::max_frames (gpu_blit)");
+      }
+      check(rb_upload(ctx_, stage_ + skip * pixels, slot0 + skip, total - skip));
+      check(rb_register(ctx_, slot0, total, offsets_, medians_));
 
       for (std::size_t i{0}; i < frames.size(); ++i) {
         auto& frame{frames[i]};
@@ -159,7 +174,14 @@ public:
         }
 
         auto& [no, image]{frame};
-        current_->blit(position_, image, {comp(image), comp(median)}, no); // src/frc.hpp:129-135
+        if (opt_.gpu_blit) { // same record as fragment::blit leaves (src/fgm.hpp:96), the dots come later
+          pending_.emplace_back(no, position_, fgm::packed_data{comp(image), comp(median)});
+          slots_.push_back(static_cast<std::uint32_t>(count_));
+        }
+        else {
+          current_->blit(position_, image, {comp(image), comp(median)}, no); // src/frc.hpp:129-135
+        }
+        ++count_;
 
         if (!init) { // the reference does not call back for the first frame (src/frc.hpp:83-95)
           grid_type keys{allocator_t<char>{alloc}};
@@ -181,7 +203,8 @@ public:
     return *current_;
   }
 
-  [[nodiscard]] inline std::list<fgm::fragment> complete() noexcept {
+  [[nodiscard]] inline std::list<fgm::fragment> complete() {
+    finish_fragment();
     for (auto& fragment : fragments_) {
       fragment.normalize();
     }
@@ -191,8 +214,65 @@ public:
 
 private:
   inline void add_fragment(mrl::dimensions_t dimension) {
+    finish_fragment();
     current_ = &fragments_.emplace_back(dimension);
     position_.x_ = position_.y_ = 0;
+  }
+
+  // gpu_blit: the fragment that just ended gets its dots from rb_blit_blend.  The map geometry is what
+  // fragment::ensure / extend would have produced frame by frame (src/fgm.hpp:190-233): the map grows in
+  // whole frame-sized steps and zero_ moves with it.
+  void finish_fragment() {
+    if (!opt_.gpu_blit || current_ == nullptr || pending_.empty()) {
+      return;
+    }
+
+    std::int64_t zero[2]{0, 0};
+    std::int64_t dim[2]{static_cast<std::int64_t>(dimensions_.width_), static_cast<std::int64_t>(dimensions_.height_)};
+    std::int64_t const step[2]{dim[0], dim[1]};
+    auto round{[](std::int64_t change, std::int64_t st) { // fragment::get_step, src/fgm.hpp:228-233
+      auto rest{change % st};
+      return (change - rest) + (rest != 0 ? st : 0);
+    }};
+    for (auto const& f : pending_) {
+      std::int64_t const p[2]{f.position_.x_, f.position_.y_};
+      for (int k{0}; k < 2; ++k) {
+        std::int64_t lo{0}, hi{0};
+        if (p[k] < zero[k]) {
+          lo = round(zero[k] - p[k], step[k]);
+        }
+        if (auto required{p[k] + step[k]}; required > 0 && required > zero[k] + dim[k]) {
+          hi = round(required - (zero[k] + dim[k]), step[k]);
+        }
+        zero[k] -= lo;
+        dim[k] += lo + hi;
+      }
+    }
+
+    std::vector<rb_placement> places(pending_.size());
+    for (std::size_t i{0}; i < pending_.size(); ++i) {
+      places[i].frame = slots_[i];
+      places[i].x = static_cast<std::int32_t>(pending_[i].position_.x_ - zero[0]);
+      places[i].y = static_cast<std::int32_t>(pending_[i].position_.y_ - zero[1]);
+    }
+
+    fgm::fragment::matrix_type dots{
+        mrl::dimensions_t{static_cast<std::size_t>(dim[0]), static_cast<std::size_t>(dim[1])}};
+    check(rb_blit_blend(ctx_,
+                        places.data(),
+                        places.size(),
+                        static_cast<std::uint32_t>(dim[0]),
+                        static_cast<std::uint32_t>(dim[1]),
+                        reinterpret_cast<std::uint16_t*>(dots.data()),
+                        nullptr,
+                        nullptr));
+
+    *current_ = fgm::fragment{std::move(dots),
+                              dimensions_,
+                              fgm::point_t{static_cast<std::int32_t>(zero[0]), static_cast<std::int32_t>(zero[1])},
+                              std::move(pending_)};
+    pending_.clear();
+    slots_.clear();
   }
 
   // kpr::grid as kpe::extractor would have filled it (src/kpe.hpp:225-229,301-303)
@@ -238,6 +318,10 @@ private:
   rb_offset* offsets_{nullptr};
   std::vector<std::uint8_t> carry_;
   std::vector<rb_keypoint> kps_;
+
+  std::size_t count_{0};               // frames collected so far (== store slot with gpu_blit)
+  std::vector<fgm::frame> pending_;    // gpu_blit: frames of the current fragment, dots still to come
+  std::vector<std::uint32_t> slots_;
 
   fgm::point_t position_{};
 

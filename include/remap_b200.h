@@ -144,6 +144,20 @@ int rb_foreground_mask(rb_ctx* ctx, const uint8_t* bg, uint32_t bgW, uint32_t bg
 int rb_foreground_mask_resident(rb_ctx* ctx, const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px,
                                 int32_t py, size_t frame, uint8_t* out_mask);
 
+/* Map assembly.  fgm::fragment::blit of n frames of the resident store into one
+ * fragment's dot map (src/fgm.hpp:87-97,176-188: ++dots[pos + xy][colour], uint16 counters that wrap) and
+ * fgm::fragment::blend of the result (src/fgm.hpp:115-135: first colour with the largest count, mask =
+ * pixel ever covered).  placements[i] = (frame slot, x, y) with (x, y) the frame's position inside the
+ * map, i.e. fgm::frame::position_ minus the fragment's zero (the caller replays fragment::ensure,
+ * src/fgm.hpp:190-233, to get zero and the map size; include/frc_b200.hpp does).  Any output may be NULL.
+ * out_dots: mapH*mapW*16 uint16, out_image / out_mask: mapH*mapW bytes. */
+typedef struct rb_placement {
+  uint32_t frame;
+  int32_t x, y;
+} rb_placement;
+int rb_blit_blend(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH, uint16_t* out_dots,
+                  uint8_t* out_image, uint8_t* out_mask);
+
 /* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
  * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */
 const rb_offset* rb_offsets_device(rb_ctx* ctx);

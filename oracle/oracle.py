@@ -152,3 +152,39 @@ def foreground_mask(bg, px, py, frame):
     mask = np.zeros((H, W), np.uint8)
     lib().ro_foreground_mask(_p(bg), bw, bh, px, py, _p(frame), W, H, _p(mask))
     return mask
+
+
+def assemble_fragment(frames, pos):
+    """TEST ORACLE for map assembly: fgm::fragment::blit of every frame, one by one, with the map growing
+    exactly as the reference grows it (src/fgm.hpp:87-97,176-233; mrl::matrix::extend src/mrl.hpp:131-147),
+    then fragment::blend (src/fgm.hpp:115-135).  Plain numpy, small cases only.
+    frames: (n, H, W) uint8 0..15, pos: (n, 2) positions of one fragment.
+    -> dict(zero=(x, y), dots (mh, mw, 16) uint16, image, mask)"""
+    n, H, W = frames.shape
+    zero = [0, 0]
+    dots = np.zeros((H, W, 16), np.uint16)
+    ar = np.arange(16, dtype=np.uint8)
+    for f in range(n):
+        px, py = int(pos[f][0]), int(pos[f][1])
+        grow = [0, 0, 0, 0]  # left, top, right, bottom
+        for k, (p, step) in enumerate(((px, W), (py, H))):
+            dim = dots.shape[1 - k]
+            if p < zero[k]:
+                ch = zero[k] - p
+                grow[k] = ch - ch % step + (step if ch % step else 0)
+            required = p + step
+            if required > 0 and required > zero[k] + dim:
+                ch = required - (zero[k] + dim)
+                grow[k + 2] = ch - ch % step + (step if ch % step else 0)
+            zero[k] -= grow[k]
+        if any(grow):
+            nd = np.zeros((dots.shape[0] + grow[1] + grow[3], dots.shape[1] + grow[0] + grow[2], 16), np.uint16)
+            nd[grow[1]:grow[1] + dots.shape[0], grow[0]:grow[0] + dots.shape[1]] = dots
+            dots = nd
+        ax, ay = px - zero[0], py - zero[1]
+        onehot = (frames[f][:, :, None] == ar[None, None, :]).astype(np.uint16)
+        dots[ay:ay + H, ax:ax + W] += onehot  # uint16 arithmetic wraps like the reference's counters
+    best = dots.max(axis=2)
+    image = np.where(best != 0, dots.argmax(axis=2), 0).astype(np.uint8)  # argmax = first largest
+    mask = (best != 0).astype(np.uint8)
+    return dict(zero=(zero[0], zero[1]), dots=dots, image=image, mask=mask)

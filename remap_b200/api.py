@@ -14,6 +14,7 @@ from . import _lib
 OFFSET_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("flags", "<u4")])
 KEYPOINT_DTYPE = np.dtype([("code", "u1", (13,)), ("weight", "u1"), ("x", "<u2"), ("y", "<u2"),
                            ("region_mask", "<u4")], align=True)
+PLACEMENT_DTYPE = np.dtype([("frame", "<u4"), ("x", "<i4"), ("y", "<i4")])
 BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
 VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
                        ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
@@ -160,6 +161,18 @@ class Registrar:
                                                           bg.shape[0], px, py, frame_index,
                                                           out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def blit_blend(self, placements, map_w, map_h, want_dots=True):
+        """fgm::fragment::blit of the placed resident frames + blend.  placements: PLACEMENT_DTYPE array
+        (frame slot, x, y inside the map).  -> (dots (map_h, map_w, 16) uint16 | None, image, mask)"""
+        pl = np.ascontiguousarray(placements, PLACEMENT_DTYPE)
+        dots = np.zeros((map_h, map_w, 16), np.uint16) if want_dots else None
+        image = np.zeros((map_h, map_w), np.uint8)
+        mask = np.zeros((map_h, map_w), np.uint8)
+        self._check(self._lib.rb_blit_blend(self._ctx, pl.ctypes.data_as(C.c_void_p), len(pl), map_w, map_h,
+                                            dots.ctypes.data_as(C.c_void_p) if want_dots else None,
+                                            image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
+        return dots, image, mask
 
     # -- introspection ------------------------------------------------------------------------
     @property

@@ -18,11 +18,13 @@
 #include "rb_kpm.cuh"
 #include "rb_kpm_fast.cuh"
 #include "rb_prep.cuh"
+#include "rb_blit.cuh"
 
 static_assert(sizeof(rb_region_vote) == sizeof(RbRegionVote), "ABI mirror of RbRegionVote");
 static_assert(sizeof(rb_bin) == sizeof(RbBin), "ABI mirror of RbBin");
 static_assert(sizeof(rb_keypoint) == 24, "rb_keypoint layout");
 static_assert(sizeof(rb_offset) == 12, "rb_offset layout");
+static_assert(sizeof(rb_placement) == sizeof(RbPlacement), "ABI mirror of RbPlacement");
 
 // ---- small kernels ------------------------------------------------------------------------------
 
@@ -192,6 +194,10 @@ struct rb_ctx {
   RbBin* d_tap_bins;
   uint32_t* d_tap_count;
   rb_keypoint* d_kps;
+  RbPlacement* d_places;  // rb_blit_blend scratch (grown on demand)
+  size_t places_cap;
+  uint8_t* d_map;         // dots (32 B / map pixel) + image + mask
+  size_t map_cap;
   uint8_t* d_bg;       // scratch for rb_foreground_mask
   size_t bg_cap;
   uint8_t* d_fgframe;  // dense frame scratch
@@ -446,7 +452,7 @@ void rb_destroy(rb_ctx* c) {
   cudaFree(c->d_frames4); cudaFree(c->d_lists); cudaFree(c->d_counts); cudaFree(c->d_deferred); cudaFree(c->d_deferred2); cudaFree(c->d_work);
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
-  cudaFree(c->d_kps); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
+  cudaFree(c->d_kps); cudaFree(c->d_places); cudaFree(c->d_map); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
   for (int i = 0; i < 6; ++i)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (int i = 0; i < 2; ++i)
@@ -848,6 +854,47 @@ int rb_region_votes(rb_ctx* c, size_t pair, uint32_t region, rb_bin* out, size_t
     RB_CUDA(c, cudaMemcpyAsync(out, c->d_tap_bins, m * sizeof(rb_bin), cudaMemcpyDeviceToHost, c->stream));
     RB_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  return RB_OK;
+}
+
+int rb_blit_blend(rb_ctx* c, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH, uint16_t* out_dots,
+                  uint8_t* out_image, uint8_t* out_mask) {
+  if (!c || (!placements && n) || mapW == 0 || mapH == 0) return RB_ERR_INVALID;
+  const RbGeom& g = c->g;
+  for (size_t i = 0; i < n; ++i) {
+    const rb_placement& p = placements[i];
+    if (p.frame >= c->uploaded) { c->err = "rb_blit_blend: frame not uploaded"; return RB_ERR_STATE; }
+    if (p.x < 0 || p.y < 0 || (uint64_t)p.x + g.W > mapW || (uint64_t)p.y + g.H > mapH) {
+      c->err = "rb_blit_blend: a frame lies outside the map";
+      return RB_ERR_INVALID;
+    }
+  }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  if (n > c->places_cap) {
+    if (c->d_places) { cudaFree(c->d_places); c->bytes -= c->places_cap * sizeof(RbPlacement); c->d_places = nullptr; }
+    c->places_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_places, n * sizeof(RbPlacement)));
+    c->places_cap = n;
+  }
+  const size_t px = (size_t)mapW * mapH, need = px * 34 + 256;
+  if (need > c->map_cap) {
+    if (c->d_map) { cudaFree(c->d_map); c->bytes -= c->map_cap; c->d_map = nullptr; }
+    c->map_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_map, need));
+    c->map_cap = need;
+  }
+  uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
+  uint8_t* d_img = c->d_map + px * 32;
+  uint8_t* d_msk = d_img + px;
+  if (n) RB_CUDA(c, cudaMemcpyAsync(c->d_places, placements, n * sizeof(RbPlacement), cudaMemcpyHostToDevice, c->stream));
+  const dim3 grid((mapW + RB_BLIT_TX - 1) / RB_BLIT_TX, (mapH + RB_BLIT_TY - 1) / RB_BLIT_TY);
+  rb_blit_blend_kernel<<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places, (uint32_t)n,
+                                                           mapW, mapH, d_dots, d_img, d_msk);
+  RB_LAUNCHED(c, "rb_blit_blend_kernel");
+  if (out_dots) RB_CUDA(c, cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
+  if (out_mask) RB_CUDA(c, cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RB_OK;
 }
 

@@ -92,3 +92,33 @@ def positions(offsets) -> np.ndarray:
     start = np.maximum.accumulate(start)
     out = np.stack([frag, cx - cx[start], cy - cy[start]], 1).astype(np.int32)
     return out
+
+
+def fragment_extents(pos, width: int, height: int):
+    """The dot-map geometry fgm::fragment ends up with after blitting frames at `pos` in order
+    (src/fgm.hpp:190-233: ensure/extend grow the map in whole frame-sized steps, `zero_` moves with it).
+
+    pos: (n, 2) int positions of ONE fragment (as frc::collector accumulates them, first frame at 0, 0).
+    -> (zero_x, zero_y, map_w, map_h); a frame at pos p lies at p - zero inside the map."""
+    zero = [0, 0]
+    dim = [width, height]  # fragment(step) starts with a map of one step (src/fgm.hpp:44-47)
+    step = (width, height)
+    for p in np.asarray(pos, np.int64):
+        for k in (0, 1):
+            lo = hi = 0
+            if p[k] < zero[k]:  # src/fgm.hpp:207-211
+                lo = _round_up_step(zero[k] - int(p[k]), step[k])
+            required = int(p[k]) + step[k]  # src/fgm.hpp:213-221
+            if required > 0:
+                limit = zero[k] + dim[k]
+                if required > limit:
+                    hi = _round_up_step(required - limit, step[k])
+            zero[k] -= lo  # src/fgm.hpp:223
+            dim[k] += lo + hi  # matrix::extend, src/mrl.hpp:131-147
+    return zero[0], zero[1], dim[0], dim[1]
+
+
+def _round_up_step(change: int, step: int) -> int:
+    """fgm::fragment::get_step (src/fgm.hpp:228-233)"""
+    rest = change % step
+    return (change - rest) + (step if rest else 0)

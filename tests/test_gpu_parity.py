@@ -246,3 +246,60 @@ def test_errors_are_reported_not_thrown():
             reg.upload(np.zeros((5, 224, 320), np.uint8))  # beyond capacity
     with pytest.raises(remap_b200.RemapError):
         remap_b200.Registrar(16, 16, max_frames=4)  # too small for the 4x2 grid
+
+
+def _assemble_on_gpu(frames, pos):
+    from remap_b200 import PLACEMENT_DTYPE, shard
+    n, H, W = frames.shape
+    zx, zy, mw, mh = shard.fragment_extents(pos, W, H)
+    pl = np.zeros(n, PLACEMENT_DTYPE)
+    pl["frame"] = np.arange(n)
+    pl["x"] = pos[:, 0] - zx
+    pl["y"] = pos[:, 1] - zy
+    with remap_b200.Registrar(W, H, max_frames=max(n, 2)) as reg:
+        reg.upload(frames)
+        dots, image, mask = reg.blit_blend(pl, mw, mh)
+    return (zx, zy), dots, image, mask
+
+
+@pytest.mark.parametrize("case", ["scroll", "back_and_forth", "wrap"])
+def test_map_assembly_blit_blend_matches_reference_semantics(case):
+    """rb_blit_blend (gathered, no atomics) == fragment::blit frame by frame + blend, including the way the
+    reference grows the map (frame-sized steps) and the uint16 wrap of the counters."""
+    if case == "scroll":
+        seq = synth.scrolling_tilemap(120, 320, 224, seed=21, vmax=(9, 7))
+        frames, pos = seq.frames, shard_positions(seq)
+    elif case == "back_and_forth":
+        seq = synth.scrolling_tilemap(60, 200, 136, seed=22, vmax=(30, 20))
+        frames = np.concatenate([seq.frames, seq.frames[::-1]])
+        p = shard_positions(seq)
+        pos = np.concatenate([p, p[::-1]])
+        pos = pos - np.array([[150, -90]])  # negative and positive excursions around the first frame
+        pos[0] = 0
+    else:  # one small frame placed 65,540 times on the same spot: the counters wrap past 65,535
+        rng = np.random.default_rng(23)
+        frames = np.repeat(rng.integers(0, 16, size=(1, 40, 64), dtype=np.uint8), 70, axis=0)
+        pos = np.zeros((70, 2), np.int64)
+    zero, dots, image, mask = _assemble_on_gpu(frames, pos)
+    if case == "wrap":
+        # 70 placements are cheap to check exactly; the wrap itself needs > 65,535 visits: repeat the list
+        from remap_b200 import PLACEMENT_DTYPE
+        n_rep = 65540
+        pl = np.zeros(n_rep, PLACEMENT_DTYPE)
+        with remap_b200.Registrar(64, 40, max_frames=2) as reg:
+            reg.upload(frames[:2])
+            dots, image, mask = reg.blit_blend(pl, 64, 40)
+        want = np.zeros((40, 64, 16), np.uint16)
+        np.put_along_axis(want, frames[0][:, :, None].astype(np.int64), np.uint16(n_rep % 65536), axis=2)
+        assert np.array_equal(dots, want)
+        assert np.array_equal(image, frames[0]) and mask.all()  # 4 != 0: still the only non-zero bin
+        return
+    want = oracle.assemble_fragment(frames, pos)
+    assert zero == want["zero"] and dots.shape == want["dots"].shape
+    assert np.array_equal(dots, want["dots"])
+    assert np.array_equal(image, want["image"]) and np.array_equal(mask, want["mask"])
+
+
+def shard_positions(seq):
+    """positions as frc::collector accumulates them from the true offsets (first frame at 0, 0)"""
+    return np.concatenate([[[0, 0]], np.cumsum(seq.true_offsets, axis=0)]).astype(np.int64)

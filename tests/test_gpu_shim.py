@@ -18,13 +18,13 @@ SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
 pytestmark = pytest.mark.gpu
 
 
-def _run(frames, batch, fill, tmp_path):
+def _run(frames, batch, fill, tmp_path, gpu_blit=False):
     if not os.path.exists(SHIM):
         pytest.fail("oracle/_ref/shim_harness missing: run `python oracle/build_ref.py` in the build container")
     n, H, W = frames.shape
     path = os.path.join(tmp_path, "frames.bin")
     np.ascontiguousarray(frames, np.uint8).tofile(path)
-    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill))], capture_output=True,
+    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill)), str(int(gpu_blit))], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
     assert r.stdout.startswith("IDENTICAL"), r.stdout
@@ -48,3 +48,12 @@ def test_collector_shim_scene_cuts_open_fragments(tmp_path):
 def test_collector_shim_odd_size_and_long_run(tmp_path):
     seq = synth.scrolling_tilemap(300, 323, 227, seed=9)
     _run(seq.frames, 128, False, str(tmp_path))
+
+
+@pytest.mark.parametrize("batch", [5, 64])
+def test_collector_shim_with_gpu_map_assembly(batch, tmp_path):
+    """options::gpu_blit: the fragments' dot maps come from rb_blit_blend instead of fragment::blit on the host
+    and must be identical to the reference collector's, fragment for fragment (zero, size, every histogram)."""
+    seq = synth.scrolling_tilemap(120, 320, 224, seed=13, cut_every=45, vmax=(9, 7))
+    out = _run(seq.frames, batch, False, str(tmp_path), gpu_blit=True)
+    assert "dots from rb_blit_blend" in out and int(out.split()[1]) >= 2, out
