@@ -357,6 +357,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     f.box_x = bx;
     f.nbox_y = (by + 255) / 256;
     f.box_y = (by + f.nbox_y - 1) / f.nbox_y;
+    if (f.nbox_y > 1) f.box_y = rb_align_up(f.box_y, 8);  // every box must land 128-byte aligned in shared memory
     uint32_t dxbits = 0, dybits = 0;
     while ((1u << dxbits) <= 2 * g.W) ++dxbits;  // dx + W < 2 W, never all ones
     while ((1u << dybits) <= 2 * g.H) ++dybits;

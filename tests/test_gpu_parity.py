@@ -59,8 +59,20 @@ ORACLE_CASES = {
     "cuts": (lambda: synth.scrolling_tilemap(8, 320, 224, seed=39, cut_every=3, levels=2).frames, {}),
     "sprites": (lambda: synth.scrolling_tilemap(5, 320, 224, seed=40, sprites=12).frames, {}),
     "zeros": (lambda: np.zeros((3, 224, 320), np.uint8), {}),
+    # tall regions: the matcher's tile needs two stacked TMA boxes (more than 256 rows per region)
+    "tall_1024x768": (lambda: synth.scrolling_tilemap(3, 1024, 768, seed=43, speckle=0.01, vmax=(20, 15)).frames, {}),
+    "tall_320x600": (lambda: synth.scrolling_tilemap(4, 320, 600, seed=44, world_h=1024).frames, {}),
+    "one_region_active": (lambda: _one_corner_textured(), {}),
     "two_frames": (lambda: synth.scrolling_tilemap(2, 320, 224, seed=41).frames, {}),
 }
+
+
+def _one_corner_textured():
+    """texture only in the top-left corner: a single active region -> kpm::match gives up (src/kpm.hpp:401)"""
+    f = synth.scrolling_tilemap(3, 320, 224, seed=45).frames.copy()
+    f[:, :, 80:] = 0
+    f[:, 110:, :] = 0
+    return f
 
 
 # matcher variants: the pipelined matcher (default), the general kernel alone, the pipelined matcher with
@@ -131,6 +143,25 @@ def test_pipelined_host_registration_equals_upload_then_register(chunk, size):
     assert np.array_equal(off_a, off_b) and np.array_equal(med_a, med_b)
     for fld in ballots_a.dtype.names:
         assert np.array_equal(ballots_a[fld], ballots_b[fld]), fld
+
+
+def test_single_frame_and_two_frame_registrations():
+    """n = 1: extraction only, no pair; n = 2: one pair; through both entry points."""
+    seq = synth.scrolling_tilemap(2, 320, 224, seed=46)
+    cfg = oracle.config(320, 224)
+    med0, kps0 = oracle.extract(cfg, seq.frames[0])
+    with remap_b200.Registrar(320, 224, max_frames=4) as reg:
+        reg.upload(seq.frames[:1])
+        off, med = reg.register(1, want_medians=True)
+        assert len(off) == 0 and np.array_equal(med[0], med0)
+        assert np.array_equal(reg.keypoints(0)["code"], kps0["code"])
+        reg.register_host_async(seq.frames[:1], first=1)
+        assert len(reg.fetch_offsets(0)) == 0
+        assert np.array_equal(reg.fetch_medians(1, first=1)[0], med0)
+        reg.register_host_async(seq.frames, first=2)
+        off2 = reg.fetch_offsets(1)
+        assert (int(off2["dx"][0]), int(off2["dy"][0])) == tuple(int(v) for v in seq.true_offsets[0])
+        assert off2["flags"][0] & RB_OFFSET_VALID
 
 
 def test_dirty_high_nibbles_are_ignored():
