@@ -127,28 +127,25 @@ RB_HD void rank_planes(uint32_t t4, uint32_t t3, uint32_t t2, uint32_t t1, uint3
     const uint32_t m0 = a0 << 1, n0 = a0 << 2, m1 = a1 << 1, n1 = a1 << 2;
     q3 = (rb_maj(a1, m1, n1) | ((a1 | m1 | n1) & rb_maj(a0, m0, n0))) << 1;
   }
-  // 5x5: S = U + 2 V + 4 W with U, V, W the 5-wide horizontal popcounts of b0, b1, b2; columns i-4 .. i
+  // 5x5: S = sum over columns i-4 .. i of the column count b2 b1 b0.  Only S >= 12 is wanted, i.e.
+  // (S >> 2) >= 3, so each bit position is reduced with full adders just far enough to hand its
+  // carries up; sum bits that cannot reach bit 2 are never formed.
   {
-    // U: only its 2s and 4s bits matter for S >= 12
+    // weight 1: five b0 bits -> two carries of weight 2
     uint32_t e1 = b0 << 1, e2 = b0 << 2, e3 = b0 << 3, e4 = b0 << 4;
-    uint32_t s = rb_xor3(b0, e1, e2), k = rb_maj(b0, e1, e2), k2 = rb_maj(s, e3, e4);
-    const uint32_t u1 = k ^ k2, u2 = k & k2;
+    const uint32_t s = rb_xor3(b0, e1, e2), k = rb_maj(b0, e1, e2), k2 = rb_maj(s, e3, e4);
+    // weight 2: five b1 bits + k + k2 -> three carries of weight 4
     e1 = b1 << 1; e2 = b1 << 2; e3 = b1 << 3; e4 = b1 << 4;
-    s = rb_xor3(b1, e1, e2); k = rb_maj(b1, e1, e2);
-    const uint32_t v0 = rb_xor3(s, e3, e4);
-    k2 = rb_maj(s, e3, e4);
-    const uint32_t v1 = k ^ k2, v2 = k & k2;
+    const uint32_t t1 = rb_xor3(b1, e1, e2), c1 = rb_maj(b1, e1, e2);
+    const uint32_t t2 = rb_xor3(t1, e3, e4), c2 = rb_maj(t1, e3, e4);
+    const uint32_t c3 = rb_maj(t2, k, k2);
+    // weight 4: five b2 bits + c1 + c2 + c3 = N ones; S >= 12 <=> N >= 3
     e1 = b2 << 1; e2 = b2 << 2; e3 = b2 << 3; e4 = b2 << 4;
-    s = rb_xor3(b2, e1, e2); k = rb_maj(b2, e1, e2);
-    const uint32_t w0 = rb_xor3(s, e3, e4);
-    k2 = rb_maj(s, e3, e4);
-    const uint32_t w1 = k ^ k2, w2 = k & k2;
-    // A column's count is <= 5, so its 2s and 4s bits are never both set: Z = V + 2 W <= 10 and
-    // S = U + 2 Z.  S >= 12  <=>  Z >= 6, or Z == 5 and U >= 2, or Z == 4 and U >= 4.
-    const uint32_t z1 = v1 ^ w0, k1 = v1 & w0;
-    const uint32_t z2 = rb_xor3(v2, w1, k1), z3 = w2 | rb_maj(v2, w1, k1);
-    const uint32_t ok45 = u2 | (v0 & u1);          // Z odd (== 5): U >= 2 ; Z even (== 4): U >= 4
-    q5 = z3 | (z2 & (z1 | ok45));                  // z3: Z >= 8 ; z2 & z1: Z in 6..7 ; z2 & !z1: Z in 4..5
+    const uint32_t g1 = rb_xor3(b2, e1, e2), d1 = rb_maj(b2, e1, e2);
+    const uint32_t g2 = rb_xor3(e3, e4, c1), d2 = rb_maj(e3, e4, c1);
+    const uint32_t g3 = rb_xor3(c2, c3, g1), d3 = rb_maj(c2, c3, g1);
+    // N = g2 + g3 + 2 (d1 + d2 + d3) >= 3  <=>  two of the d's, or one d and one g
+    q5 = rb_maj(d1, d2, d3) | ((d1 | d2 | d3) & (g2 | g3));
   }
 }
 
