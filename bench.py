@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4000, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap-batches", type=int, default=0, help="rb_config.overlap_batches (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -210,7 +211,7 @@ def main():
     n = seq.frames.shape[0]
     stream = torch.cuda.Stream(device=dev)
     reg = remap_b200.Registrar(args.width, args.height, max_frames=n, device=local_rank, compute_median=True,
-                               profile=True, stream=stream.cuda_stream)
+                               profile=True, stream=stream.cuda_stream, overlap_batches=args.overlap_batches)
     # pinned host copy of the frames (source of the e2e path; also the one-off resident upload)
     pinned = torch.empty((n, args.height, args.width), dtype=torch.uint8, pin_memory=True)
     pinned.numpy()[...] = seq.frames

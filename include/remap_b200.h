@@ -60,6 +60,9 @@ typedef struct rb_config {
                                matcher (<= 2047); longer lists are deferred                   */
   uint32_t run_pairs;       /* 0 = auto; consecutive pairs per work item of the matcher      */
   uint32_t upload_chunk;    /* 0 = auto; frames per host->device chunk of rb_register_host_async */
+  uint32_t overlap_batches; /* 0 = auto (1 = K1 then matcher, one after the other); > 1: batches per call, K1 of
+                               batch b + 1 on a second stream concurrently with the matcher of batch b (slower
+                               on B200 as measured; kept for experiments)                                     */
 } rb_config;
 
 /* == std::optional<cdt::offset_t> returned by kpm::match (src/kpm.hpp:395-415), plus flags. */

@@ -32,7 +32,7 @@ class RbConfig(C.Structure):
                 ("device", C.c_int32), ("max_frames", C.c_uint32), ("compute_median", C.c_uint32),
                 ("code_slots", C.c_uint32), ("offset_slots", C.c_uint32), ("profile", C.c_uint32),
                 ("stream", C.c_void_p), ("kpm_mode", C.c_uint32), ("list_cap", C.c_uint32),
-                ("run_pairs", C.c_uint32), ("upload_chunk", C.c_uint32)]
+                ("run_pairs", C.c_uint32), ("upload_chunk", C.c_uint32), ("overlap_batches", C.c_uint32)]
 
 
 class RemapLibraryMissing(RuntimeError):

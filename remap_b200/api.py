@@ -37,7 +37,7 @@ class Registrar:
 
     def __init__(self, width, height, max_frames, device=0, compute_median=True, profile=False, stream=None,
                  code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3,
-                 kpm_mode=0, list_cap=0, run_pairs=0, upload_chunk=0):
+                 kpm_mode=0, list_cap=0, run_pairs=0, upload_chunk=0, overlap_batches=0):
         self._lib = _lib.load()
         cfg = _lib.RbConfig()
         self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
@@ -49,6 +49,7 @@ class Registrar:
         cfg.code_slots, cfg.offset_slots = code_slots, offset_slots
         cfg.stream = stream
         cfg.kpm_mode, cfg.list_cap, cfg.run_pairs, cfg.upload_chunk = kpm_mode, list_cap, run_pairs, upload_chunk
+        cfg.overlap_batches = overlap_batches
         self.width, self.height, self.max_frames = width, height, max_frames
         self.nreg = grid[0] * grid[1]
         self._ctx = C.c_void_p()

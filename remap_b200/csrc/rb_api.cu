@@ -162,6 +162,12 @@ __global__ void __launch_bounds__(256) rb_kpm_deferred_kernel(const RbKpmParams 
 }
 
 // ---- context ------------------------------------------------------------------------------------
+#define RB_MAX_BATCHES 16
+
+// profile marks of one batch: K1 start / end on the extraction stream; matcher start, after K1c, after
+// K2, after the deferred / general kernel, after K3 on the main stream
+struct RbBatchEvents { cudaEvent_t e[7]; };
+
 
 struct rb_ctx {
   rb_config cfg;
@@ -207,7 +213,10 @@ struct rb_ctx {
   size_t kpm_smem;
   size_t uploaded;       // frames [0, uploaded) hold data
   size_t reg_first, reg_n;
-  cudaEvent_t ev[6];      // profile marks: start, after K1, after K1c, after K2, after deferred/general, end
+  RbBatchEvents bev[RB_MAX_BATCHES];  // profile marks per batch of the last call
+  size_t nbatch_used;
+  cudaStream_t kpe_stream;   // K1 runs here, concurrently with the matcher of the previous batch
+  cudaEvent_t ev_kpe[RB_MAX_BATCHES];
   cudaStream_t copy_stream;  // host -> device copies of rb_register_host_async
   cudaEvent_t ev_copy[2], ev_entry;
   uint8_t* h_stage[2];     // pinned staging: two chunks of packed 4 bit/pixel frames
@@ -299,7 +308,15 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   RB_CUDA(c, cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
   if (cfg->stream) { c->stream = static_cast<cudaStream_t>(cfg->stream); c->own_stream = false; }
   else { RB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-  for (int i = 0; i < 6; ++i) RB_CUDA(c, cudaEventCreate(&c->ev[i]));
+  for (int b = 0; b < RB_MAX_BATCHES; ++b) {
+    for (int i = 0; i < 7; ++i) RB_CUDA(c, cudaEventCreate(&c->bev[b].e[i]));
+    RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_kpe[b], cudaEventDisableTiming));
+  }
+  {
+    int lo = 0, hi = 0;  // numerically larger = lower priority: the matcher's CTAs get SM resources first
+    RB_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RB_CUDA(c, cudaStreamCreateWithPriority(&c->kpe_stream, cudaStreamNonBlocking, lo));
+  }
   RB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
   RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
@@ -454,8 +471,12 @@ void rb_destroy(rb_ctx* c) {
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_places); cudaFree(c->d_map); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
-  for (int i = 0; i < 6; ++i)
-    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int b = 0; b < RB_MAX_BATCHES; ++b) {
+    for (int i = 0; i < 7; ++i)
+      if (c->bev[b].e[i]) cudaEventDestroy(c->bev[b].e[i]);
+    if (c->ev_kpe[b]) cudaEventDestroy(c->ev_kpe[b]);
+  }
+  if (c->kpe_stream) { cudaStreamSynchronize(c->kpe_stream); cudaStreamDestroy(c->kpe_stream); }
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
   if (c->ev_entry) cudaEventDestroy(c->ev_entry);
@@ -573,31 +594,32 @@ static uint32_t pick_segments(const rb_ctx* c, size_t n) {
   return best;
 }
 
-// Enqueues the registration of frames [first, first + n) on the context's stream: K1 on frames
-// [kpe_first, first + n) (earlier ones were extracted by a previous call), the matcher on the n - 1
-// pairs, K3.  Ballots, results and offsets are stored at the pair's absolute index (= index of its
-// first frame).
-static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
+// K1 on frames [f0, f0 + kn), on stream `st`
+static int launch_kpe(rb_ctx* c, size_t f0, size_t kn, cudaStream_t st) {
   const RbGeom& g = c->g;
-  const bool prof = c->cfg.profile != 0;
-  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-  if (kpe_first < first + n) {
-    const size_t kn = first + n - kpe_first;
-    RbKpeParams p;
-    p.g = g;
-    p.frames = c->d_frames + g.frame_stride * kpe_first;
-    p.median = c->d_median ? c->d_median + g.median_stride * kpe_first : nullptr;
-    p.kpbits = c->d_kp + (size_t)kpe_first * g.H * g.NS;
-    p.w2bits = c->d_w2 + (size_t)kpe_first * g.H * g.NS;
-    p.nframes = (uint32_t)kn;
-    p.nseg = pick_segments(c, kn);
-    p.seg_rows = (g.H - 6 + p.nseg - 1) / p.nseg;
-    const size_t items = kn * p.nseg * g.NS;
-    const uint32_t blocks = (uint32_t)((items + 127) / 128);
-    rb_kpe_kernel<<<blocks, 128, 0, c->stream>>>(p);
-    RB_LAUNCHED(c, "rb_kpe_kernel");
-  }
-  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  RbKpeParams p;
+  p.g = g;
+  p.frames = c->d_frames + g.frame_stride * f0;
+  p.median = c->d_median ? c->d_median + g.median_stride * f0 : nullptr;
+  p.kpbits = c->d_kp + (size_t)f0 * g.H * g.NS;
+  p.w2bits = c->d_w2 + (size_t)f0 * g.H * g.NS;
+  p.nframes = (uint32_t)kn;
+  p.nseg = pick_segments(c, kn);
+  p.seg_rows = (g.H - 6 + p.nseg - 1) / p.nseg;
+  const size_t items = kn * p.nseg * g.NS;
+  const uint32_t blocks = (uint32_t)((items + 127) / 128);
+  rb_kpe_kernel<<<blocks, 128, 0, st>>>(p);
+  ++c->launches;
+  RB_CUDA(c, cudaGetLastError());
+  return RB_OK;
+}
+
+// The matcher + K3 for the n - 1 pairs of frames [first, first + n), on the main stream.  Frames
+// [list_first, first + n) still need their region lists (K1c).  Ballots, results and offsets are stored at
+// the pair's absolute index (= index of its first frame).
+static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cudaEvent_t* ev) {
+  const RbGeom& g = c->g;
+  if (ev) RB_CUDA(c, cudaEventRecord(ev[2], c->stream));
   if (n >= 2) {
     RbKpmParams p;
     memset(&p, 0, sizeof(p));
@@ -612,14 +634,14 @@ static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
     if (c->cfg.kpm_mode == 0) {
       // K1c: per-(frame, region) keypoint lists; K2: pipelined matcher; then the general kernel over
       // whatever K2 deferred (normally nothing: the grid exits on an empty list)
-      if (kpe_first < first + n) {
-        const uint32_t items = (uint32_t)(first + n - kpe_first) * g.nreg;
-        rb_list_kernel<<<(items + 7) / 8, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)kpe_first,
-                                                              (uint32_t)(first + n - kpe_first), c->fast.lcap, c->d_lists,
+      if (list_first < first + n) {
+        const uint32_t items = (uint32_t)(first + n - list_first) * g.nreg;
+        rb_list_kernel<<<(items + 7) / 8, 256, 0, c->stream>>>(g, c->d_kp, c->d_w2, (uint32_t)list_first,
+                                                              (uint32_t)(first + n - list_first), c->fast.lcap, c->d_lists,
                                                               c->d_counts);
         RB_LAUNCHED(c, "rb_list_kernel");
       }
-      if (prof) RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+      if (ev) RB_CUDA(c, cudaEventRecord(ev[3], c->stream));
       RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));  // work counter; deferred count / error word accumulate
       RbKpmFastParams f = c->fast;
       f.lists = c->d_lists;
@@ -638,7 +660,7 @@ static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
       if (grid > witems) grid = witems;
       rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
       RB_LAUNCHED(c, "rb_kpm_fast_kernel");
-      if (prof) RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+      if (ev) RB_CUDA(c, cudaEventRecord(ev[4], c->stream));
       const uint2* glist = c->d_deferred;
       const uint32_t* gcount = c->d_work + 4;
       if (c->fast2_smem) {  // second pass over what the first deferred (exits at once on an empty list)
@@ -664,18 +686,55 @@ static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
       rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, glist, gcount, f.deferred_cap, c->d_work + 1);
       RB_LAUNCHED(c, "rb_kpm_deferred_kernel");
     } else {
-      if (prof) { RB_CUDA(c, cudaEventRecord(c->ev[2], c->stream)); RB_CUDA(c, cudaEventRecord(c->ev[3], c->stream)); }
+      if (ev) { RB_CUDA(c, cudaEventRecord(ev[3], c->stream)); RB_CUDA(c, cudaEventRecord(ev[4], c->stream)); }
       rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
       RB_LAUNCHED(c, "rb_kpm_kernel");
     }
-    if (prof) RB_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+    if (ev) RB_CUDA(c, cudaEventRecord(ev[5], c->stream));
     rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, p.votes, c->d_results + first,
                                                                                    c->d_offsets + first, (uint32_t)(n - 1));
     RB_LAUNCHED(c, "rb_declare_offsets_kernel");
-  } else if (prof) {
-    for (int i = 2; i <= 4; ++i) RB_CUDA(c, cudaEventRecord(c->ev[i], c->stream));
+  } else if (ev) {
+    for (int i = 3; i <= 5; ++i) RB_CUDA(c, cudaEventRecord(ev[i], c->stream));
   }
-  if (prof) RB_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+  if (ev) RB_CUDA(c, cudaEventRecord(ev[6], c->stream));
+  return RB_OK;
+}
+
+// Enqueues the registration of frames [first, first + n): K1 on frames [kpe_first, first + n) (earlier
+// ones were extracted by a previous call), the matcher on the n - 1 pairs, K3.
+// K1 is bound by the ALU pipe and uses no shared memory; the matcher is bound by instruction issue and
+// its barrier and lives in shared memory.  With overlap_batches > 1 they run CONCURRENTLY: the frames are
+// cut into batches, K1 of batch b + 1 goes to a second, lower-priority stream while the matcher of batch
+// b runs on the main stream.  On B200 this measured SLOWER than one after the other (K1's CTAs hold the
+// whole register file of an SM, the matcher's CTAs queue behind them), so the default is 1.
+static int enqueue_range(rb_ctx* c, size_t first, size_t n, size_t kpe_first) {
+  const bool prof = c->cfg.profile != 0;
+  const size_t kn = kpe_first < first + n ? first + n - kpe_first : 0;
+  size_t nb = c->cfg.overlap_batches ? c->cfg.overlap_batches : 1;  // measured: overlapping does not pay (profiles/README.md)
+  if (nb > RB_MAX_BATCHES) nb = RB_MAX_BATCHES;
+  if (kn < nb * 512) nb = kn / 512 ? kn / 512 : 1;  // batches too small to fill the GPU gain nothing
+  c->nbatch_used = 0;
+  if (kn == 0) return launch_match(c, first, n, first + n, prof ? c->bev[0].e : nullptr);
+  // K1 must come after whatever put the frames in place on the main stream (and after earlier readers of
+  // the bit maps it will overwrite)
+  RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
+  RB_CUDA(c, cudaStreamWaitEvent(c->kpe_stream, c->ev_entry, 0));
+  for (size_t b = 0; b < nb; ++b) {
+    const size_t b0 = kpe_first + kn * b / nb, b1 = kpe_first + kn * (b + 1) / nb;
+    cudaEvent_t* ev = prof ? c->bev[b].e : nullptr;
+    if (ev) RB_CUDA(c, cudaEventRecord(ev[0], c->kpe_stream));
+    int rc = launch_kpe(c, b0, b1 - b0, c->kpe_stream);
+    if (rc != RB_OK) return rc;
+    if (ev) RB_CUDA(c, cudaEventRecord(ev[1], c->kpe_stream));
+    RB_CUDA(c, cudaEventRecord(c->ev_kpe[b], c->kpe_stream));
+    RB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_kpe[b], 0));
+    // the pairs whose second frame lies in this batch
+    const size_t m0 = b == 0 ? first : b0 - 1;
+    rc = launch_match(c, m0, b1 - m0, b0, ev);
+    if (rc != RB_OK) return rc;
+    c->nbatch_used = b + 1;
+  }
   return RB_OK;
 }
 
@@ -751,9 +810,16 @@ int rb_kernel_times(rb_ctx* c, float* ms, size_t n) {
   if (!c || !ms || n < 3) return RB_ERR_INVALID;
   if (!c->cfg.profile) { c->err = "context created without profile=1"; return RB_ERR_STATE; }
   RB_CUDA(c, cudaSetDevice(c->device));
-  RB_CUDA(c, cudaEventSynchronize(c->ev[5]));
-  float d[5];
-  for (int i = 0; i < 5; ++i) RB_CUDA(c, cudaEventElapsedTime(&d[i], c->ev[i], c->ev[i + 1]));
+  // each kernel's own elapsed time, summed over the batches of the last call (K1 of one batch and the
+  // matcher of the previous one overlap in wall time; these are durations, not a timeline)
+  float d[5] = {0, 0, 0, 0, 0};
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  const size_t nbu = c->nbatch_used ? c->nbatch_used : 1;
+  for (size_t b = 0; b < nbu; ++b) {
+    float t;
+    if (c->nbatch_used) { RB_CUDA(c, cudaEventElapsedTime(&t, c->bev[b].e[0], c->bev[b].e[1])); d[0] += t; }
+    for (int i = 1; i < 5; ++i) { RB_CUDA(c, cudaEventElapsedTime(&t, c->bev[b].e[i + 1], c->bev[b].e[i + 2])); d[i] += t; }
+  }
   const float all[6] = {d[0], d[1] + d[2] + d[3], d[4], d[1], d[2], d[3]};  // kpe, matcher total, declare, lists, match, deferred
   for (size_t i = 0; i < n && i < 6; ++i) ms[i] = all[i];
   return RB_OK;

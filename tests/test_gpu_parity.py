@@ -82,6 +82,7 @@ MATCHER_MODES = {
     "general": dict(kpm_mode=1),
     "tiny_cap": dict(list_cap=64),
     "run3": dict(run_pairs=3),
+    "overlap3": dict(overlap_batches=3),
 }
 
 
