@@ -337,9 +337,15 @@ def main():
         dom_bytes = (b_kpe if dominant == "rb_kpe_kernel" else b_kpm) * n
         achieved = dom_bytes / dom_s / 1e9
         step_s = max_ms * 1e-3 / args.steps
+        # DRAM bytes of the dominant kernel per launch: dram__bytes_read + dram__bytes_write of the ncu --set full
+        # capture committed as profiles/r1h_ncu_full_summary.csv (4,000 frames of this workload), scaled to n frames
+        ncu_bytes_per_frame = {"rb_kpe_kernel": (349.32e6 + 342.84e6) / 4000.0,
+                               "rb_kpm_fast_kernel (+ rb_list_kernel)": (213.62e6 + 7.07e6 + 87.3e6 + 45.9e6) / 4000.0}
+        traffic = ncu_bytes_per_frame[dominant] * n if (args.width, args.height) == (320, 224) else None
+        traffic_src = "profiles/r1h_ncu_full_summary.csv (ncu --set full, 4,000 frames), scaled per frame" if traffic else None
         roofline = {
             "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": dom_bytes,
             "kernel_ms": {k: v / args.steps for k, v in kt.items()},
             "kernel_share_of_step": {"kpe": kpe_s / step_s, "kpm": kpm_s / step_s},
