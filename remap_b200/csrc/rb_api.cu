@@ -43,6 +43,131 @@ __global__ void rb_declare_offsets_kernel(const RbGeom g, const RbRegionVote* vo
   offsets[i] = o;
 }
 
+// K3, cooperative: one GROUP of lanes per pair (one lane per region, group = next power of two), so a
+// 20,000-pair launch fills the GPU instead of running four warps per SM over local-memory arrays.  Same
+// arithmetic as rbm::declare_pair (rb_kpm.cuh; src/kpm.hpp:172-184,199-211 + the tie analysis of
+// DESIGN.md section 2): every lane scores its own <= 3 ticket entries against all entries of the group
+// (shuffles), the group reduces to the two best candidates and to the bounds the tie analysis needs.
+__global__ void __launch_bounds__(256) rb_declare_group_kernel(const RbGeom g, const RbRegionVote* __restrict__ votes,
+                                                               rb_offset* __restrict__ offsets, uint32_t npairs, uint32_t LP) {
+  const uint32_t lane = threadIdx.x & 31, r = lane & (LP - 1), gbase = lane - r;
+  const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) / LP;
+  const bool live = pair < npairs && r < g.nreg;
+  const uint32_t rv = g.region_votes;
+  // my region's ballot
+  uint32_t key[3] = {0, 0, 0}, info[3] = {0, 0, 0};  // info: valid | pts << 1 | hi << 3 | lo << 5 | ambiguous << 7
+  uint32_t og = 0, ncurr = 0;
+  if (live) {
+    const RbRegionVote& v = votes[(uint64_t)pair * g.nreg + r];
+    ncurr = v.n_curr;
+    const uint32_t nt = v.nticket;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k)
+      if (k < nt && k < rv) {
+        key[k] = ((uint32_t)(v.ticket[k].dx + 32768) << 16) | (uint32_t)(v.ticket[k].dy + 32768);
+        const uint32_t worst = v.nge[k] - 1;
+        const uint32_t hi = v.ngt[k] < rv ? rv - v.ngt[k] : 0u, lo = worst < rv ? rv - worst : 0u;
+        info[k] = 1u | ((rv - k) << 1) | (hi << 3) | (lo << 5) | ((v.nge[k] != v.ngt[k] + 1 ? 1u : 0u) << 7);
+      }
+    if (nt == rv && v.nge[rv - 1] > rv) og = v.ngt[rv - 1] < rv ? rv - v.ngt[rv - 1] : 0u;
+  }
+  const uint32_t gmask = LP == 32 ? 0xffffffffu : (((1u << LP) - 1u) << gbase);
+  const uint32_t active = __popc(__ballot_sync(0xffffffffu, live && ncurr > 0) & gmask);  // current grid only (src/kpm.hpp:400)
+  const bool ambiguous = (__ballot_sync(0xffffffffu, ((info[0] | info[1] | info[2]) >> 7) & 1u) & gmask) != 0;
+  // score / bounds of my entries against every entry of the group
+  uint32_t score[3] = {0, 0, 0}, HI[3] = {0, 0, 0}, LO[3] = {0, 0, 0}, og_all = 0;
+  bool rep[3] = {true, true, true};  // first occurrence of its offset in (region, rank) order
+  for (uint32_t l = 0; l < LP; ++l) {
+    const uint32_t og_l = __shfl_sync(0xffffffffu, og, gbase + l);
+    og_all += og_l;
+    bool found[3] = {false, false, false};
+#pragma unroll
+    for (uint32_t m = 0; m < 3; ++m) {
+      const uint32_t okey = __shfl_sync(0xffffffffu, key[m], gbase + l), oinf = __shfl_sync(0xffffffffu, info[m], gbase + l);
+#pragma unroll
+      for (uint32_t k = 0; k < 3; ++k)
+        if ((oinf & 1u) && okey == key[k]) {
+          score[k] += (oinf >> 1) & 3u;
+          HI[k] += (oinf >> 3) & 3u;
+          LO[k] += (oinf >> 5) & 3u;
+          found[k] = true;
+          if (l < r || (l == r && m < k)) rep[k] = false;
+        }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k)
+      if (!found[k]) HI[k] += og_l;  // off that region's ticket: it can score there only by displacing a tied entry
+  }
+  auto gmax64 = [&](unsigned long long v) {
+    for (uint32_t o = LP >> 1; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = t > v ? t : v;
+    }
+    return v;
+  };
+  auto gmax32 = [&](uint32_t v) {
+    for (uint32_t o = LP >> 1; o > 0; o >>= 1) {
+      const uint32_t t = __shfl_xor_sync(0xffffffffu, v, o);
+      v = t > v ? t : v;
+    }
+    return v;
+  };
+  // the two best candidates: score desc, dx asc, dy asc
+  unsigned long long c0 = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 3; ++k)
+    if (info[k] & 1u) {
+      const unsigned long long c = ((unsigned long long)score[k] << 32) | (0xFFFFFFFFu - key[k]);
+      c0 = c > c0 ? c : c0;
+    }
+  c0 = gmax64(c0);
+  const uint32_t bkey = 0xFFFFFFFFu - (uint32_t)c0, S0 = (uint32_t)(c0 >> 32);
+  unsigned long long c1 = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 3; ++k)
+    if ((info[k] & 1u) && key[k] != bkey) {
+      const unsigned long long c = ((unsigned long long)score[k] << 32) | (0xFFFFFFFFu - key[k]);
+      c1 = c > c1 ? c : c1;
+    }
+  c1 = gmax64(c1);
+  const uint32_t S1 = (uint32_t)(c1 >> 32), half = active / 2;  // src/kpm.hpp:206
+  bool valid = false, tie = false;
+  if (active >= g.nreg / 4 && c0 != 0) {  // src/kpm.hpp:401, :202-204
+    valid = !(c1 != 0 && S0 < S1 + half);
+    // tie sensitivity (see rbm::declare_pair)
+    uint32_t hb = 0, ha = 0, lob = 0, l1c = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k)
+      if (info[k] & 1u) {
+        ha = HI[k] > ha ? HI[k] : ha;
+        if (key[k] != bkey) hb = HI[k] > hb ? HI[k] : hb; else lob = LO[k];
+        if (rep[k]) { const uint32_t cc = (LO[k] << 8) | (r * 3 + k + 1); l1c = cc > l1c ? cc : l1c; }
+      }
+    hb = gmax32(hb); ha = gmax32(ha); lob = gmax32(lob); l1c = gmax32(l1c);
+    uint32_t l2 = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 3; ++k)
+      if ((info[k] & 1u) && rep[k] && ((LO[k] << 8) | (r * 3 + k + 1)) != l1c) l2 = LO[k] > l2 ? LO[k] : l2;
+    l2 = gmax32(l2);
+    if (ambiguous) {
+      if (valid) {
+        const uint32_t Hm = hb > og_all ? hb : og_all;
+        tie = !(lob >= Hm + (half > 1 ? half : 1));
+      } else {
+        const uint32_t Hm = ha > og_all ? ha : og_all;
+        tie = !(l2 >= 1 && Hm < l2 + half);
+      }
+    }
+  }
+  if (live && r == 0) {
+    rb_offset o;
+    o.dx = valid ? (int32_t)(bkey >> 16) - 32768 : 0;
+    o.dy = valid ? (int32_t)(bkey & 0xFFFFu) - 32768 : 0;
+    o.flags = (valid ? RB_OFFSET_VALID : 0u) | (tie ? RB_OFFSET_TIE_SENSITIVE : 0u);
+    offsets[pair] = o;
+  }
+}
+
 // Parity tap: expands K1's bit maps of one frame into rb_keypoint records in the reference's
 // insertion order (column-major: x outer, y inner; src/kpe.hpp:201-204,289-305), with the 13-byte
 // code laid out exactly as kpe::extractor::encode_keypoint does (src/kpe.hpp:342-379).
@@ -223,6 +348,7 @@ struct rb_ctx {
   size_t stage_frames;
   uint64_t launches;
   bool debug_sync;
+  bool k3_reference;
   std::string err;
 };
 
@@ -291,6 +417,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   c->cfg = *cfg;
   c->device = cfg->device;
   c->debug_sync = getenv("RB_DEBUG_SYNC") != nullptr;
+  c->k3_reference = getenv("RB_K3_REFERENCE") != nullptr;
   {  // host packer threads: this process's fair share of the host when there is one process per GPU
     const long procs = sysconf(_SC_NPROCESSORS_ONLN);
     rb_hostpack_set_threads((int)(procs > 0 ? (procs / ndev > 0 ? procs / ndev : 1) : 1));
@@ -691,9 +818,18 @@ static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cu
       RB_LAUNCHED(c, "rb_kpm_kernel");
     }
     if (ev) RB_CUDA(c, cudaEventRecord(ev[5], c->stream));
-    rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, p.votes, c->d_results + first,
-                                                                                   c->d_offsets + first, (uint32_t)(n - 1));
-    RB_LAUNCHED(c, "rb_declare_offsets_kernel");
+    if (c->k3_reference) {  // RB_K3_REFERENCE=1: one thread per pair, rbm::declare_pair as the tests' host build runs it
+      rb_declare_offsets_kernel<<<(uint32_t)((n - 1 + 127) / 128), 128, 0, c->stream>>>(g, p.votes, c->d_results + first,
+                                                                                     c->d_offsets + first, (uint32_t)(n - 1));
+      RB_LAUNCHED(c, "rb_declare_offsets_kernel");
+    } else {
+      uint32_t LP = 1;
+      while (LP < g.nreg) LP <<= 1;
+      const uint64_t threads = (uint64_t)(n - 1) * LP;
+      rb_declare_group_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, c->stream>>>(g, p.votes, c->d_offsets + first,
+                                                                                      (uint32_t)(n - 1), LP);
+      RB_LAUNCHED(c, "rb_declare_group_kernel");
+    }
   } else if (ev) {
     for (int i = 3; i <= 5; ++i) RB_CUDA(c, cudaEventRecord(ev[i], c->stream));
   }

@@ -335,3 +335,29 @@ def test_map_assembly_blit_blend_matches_reference_semantics(case):
 def shard_positions(seq):
     """positions as frc::collector accumulates them from the true offsets (first frame at 0, 0)"""
     return np.concatenate([[[0, 0]], np.cumsum(seq.true_offsets, axis=0)]).astype(np.int64)
+
+
+def test_cooperative_declare_kernel_equals_the_one_thread_per_pair_reference():
+    """K3 as launched (one lane group per pair, shuffles) against rbm::declare_pair run one thread per pair
+    (RB_K3_REFERENCE=1; the same function the CPU suite runs on the host against the oracle), on sequences
+    where the vote is close: 16-px parallax bands (tie-sensitive pairs), scene cuts, sprites."""
+    cases = [synth.scrolling_tilemap(400, 320, 224, seed=61, parallax=16),
+             synth.scrolling_tilemap(300, 320, 224, seed=62, cut_every=25, levels=3, sprites=8),
+             synth.scrolling_tilemap(200, 200, 136, seed=63, parallax=32, speckle=0.02)]
+    for seq in cases:
+        n, H, W = seq.frames.shape
+        outs = []
+        for ref in (False, True):
+            if ref:
+                os.environ["RB_K3_REFERENCE"] = "1"
+            try:
+                with remap_b200.Registrar(W, H, max_frames=n) as reg:
+                    reg.upload(seq.frames)
+                    off, _ = reg.register(n)
+                    outs.append(off.copy())
+            finally:
+                os.environ.pop("RB_K3_REFERENCE", None)
+        assert np.array_equal(outs[0], outs[1])
+        flagged = (outs[0]["flags"] & RB_OFFSET_TIE_SENSITIVE) != 0
+        valid = (outs[0]["flags"] & RB_OFFSET_VALID) != 0
+        assert valid.any() and (~valid).any() or not flagged.any()
