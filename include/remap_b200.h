@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 2
+#define RB_ABI_VERSION 3
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -160,6 +160,28 @@ typedef struct rb_placement {
 } rb_placement;
 int rb_blit_blend(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH, uint16_t* out_dots,
                   uint8_t* out_image, uint8_t* out_mask);
+
+/* Pass-2 foreground filtering of one fragment: fdf::filter (src/fdf.hpp:40-75).  For every
+ * placed frame: fde::extractor::extract (src/fde.hpp:83-103: generate_mask against the background window, the
+ * contours of the frame's MEDIAN image that hold a differing pixel -- cte::extractor, src/cte.hpp:60-166 --
+ * minus those larger than a fifth of the frame) and fde::mask (src/fde.hpp:122-146: the kept contours' pixels
+ * and enclosures); then fgm::fragment::blit with that mask (src/fgm.hpp:71-85: a pixel counts where the mask
+ * is 0) into a fresh dot map of the background's size, and blend.
+ *   placements   as for rb_blit_blend; the frames must have been registered (their median images are read
+ *                from the context's median store, as fdf decompresses frc's stored medians, src/fdf.hpp:60)
+ *   background   mapH*mapW bytes = fdf::background::image_, or NULL for what the 4-argument fdf::filter
+ *                computes itself: blend() of the plain blit of these placements (src/fdf.hpp:21-34,79-89)
+ *   out_fgmasks  n*H*W bytes, 1 = foreground (== fde::mask), or NULL     (parity tap)
+ *   out_ncontours n counts of kept contours per frame, or NULL          (parity tap)
+ * The reference's contour ids are uint16 and wrap after 65,534 contours in one frame (src/cte.hpp:20,96-98);
+ * frames beyond that are outside the contract. */
+int rb_filter_fragment(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH,
+                       const uint8_t* background, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask,
+                       uint8_t* out_fgmasks, uint32_t* out_ncontours);
+/* Last rb_filter_fragment: ms[0] background blit + blend, ms[1] foreground bit maps, ms[2] masked blit + blend;
+ * frames_deferred = frames whose runs or contours did not fit the shared-memory tables and took the
+ * global-memory variant of the same kernel. */
+int rb_filter_times(rb_ctx* ctx, float* ms, size_t n, uint32_t* frames_deferred);
 
 /* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
  * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */

@@ -52,7 +52,7 @@ PATCHES = [
 DEAD_MEMBER_RE = re.compile(
     r"\n  inline \[\[nodiscard\]\] __m256i get_unit(?:_low|_hi)?\(.*?\n  \}\n", re.S)
 
-FILES = ["all.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fgm.hpp",
+FILES = ["all.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fdf.hpp", "fgm.hpp",
          "frc.hpp", "icd.hpp", "ifd.hpp", "kpe.hpp", "kpm.hpp", "kpr.hpp", "mrl.hpp",
          "nic.hpp", "sid.hpp"]
 

@@ -24,6 +24,8 @@ VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"),
 RESULT_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("valid", "<u4"), ("tie_sensitive", "<u4"),
                          ("active", "<u4"), ("top_dx", "<i4", (2,)), ("top_dy", "<i4", (2,)),
                          ("top_score", "<u4", (2,)), ("ntop", "<u4")])
+CONTOUR_DTYPE = np.dtype([("area", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"),
+                          ("colour", "<u4")])
 
 
 class Config(C.Structure):
@@ -65,12 +67,15 @@ def lib():
         _lib.ro_foreground_mask.restype = None
         _lib.ro_foreground_mask.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.ro_foreground.restype = C.c_size_t
+        _lib.ro_foreground.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.ro_luts.restype = None
         _lib.ro_luts.argtypes = [C.c_void_p, C.c_void_p]
         _lib.ro_sections.restype = None
         _lib.ro_sections.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
         for fn, dt in (("ro_sizeof_keypoint", KP_DTYPE), ("ro_sizeof_region_vote", VOTE_DTYPE),
-                       ("ro_sizeof_match_result", RESULT_DTYPE)):
+                       ("ro_sizeof_match_result", RESULT_DTYPE), ("ro_sizeof_contour", CONTOUR_DTYPE)):
             f = getattr(_lib, fn)
             f.restype = C.c_size_t
             assert f() == dt.itemsize, (fn, f(), dt.itemsize)
@@ -188,3 +193,46 @@ def assemble_fragment(frames, pos):
     image = np.where(best != 0, dots.argmax(axis=2), 0).astype(np.uint8)  # argmax = first largest
     mask = (best != 0).astype(np.uint8)
     return dict(zero=(zero[0], zero[1]), dots=dots, image=image, mask=mask)
+
+
+def foreground(bg, px, py, frame, median):
+    """Pass-2 foreground of one frame: fde::extractor::extract + fde::mask (src/fde.hpp:83-146).
+    -> (mask (H, W) u8 0/1, kept contours in the reference's order)"""
+    bg = np.ascontiguousarray(bg, np.uint8)
+    frame = np.ascontiguousarray(frame, np.uint8)
+    median = np.ascontiguousarray(median, np.uint8)
+    bh, bw = bg.shape
+    H, W = frame.shape
+    assert 0 <= px and px + W <= bw and 0 <= py and py + H <= bh
+    mask = np.zeros((H, W), np.uint8)
+    cont = np.zeros(W * H, CONTOUR_DTYPE)
+    n = lib().ro_foreground(_p(bg), bw, bh, px, py, _p(frame), _p(median), W, H, _p(mask), _p(cont), cont.shape[0])
+    assert n != 2 ** 64 - 1, "more than 65,534 contours in one frame: undefined in the reference"
+    return mask, cont[:n].copy()
+
+
+def filter_fragment(frames, medians, pos, mapW, mapH, background=None):
+    """TEST ORACLE for fdf::filter over ONE fragment (src/fdf.hpp:40-75): background = blend of the plain
+    blit of all frames (src/fdf.hpp:21-34) unless given; per frame the pass-2 foreground mask, then the
+    masked blit (src/fgm.hpp:71-85: ++dots[colour] where mask == 0).  pos: (n, 2) positions inside the map
+    (frame position minus fragment zero).  numpy + the C restatement; small cases only.
+    -> dict(background, masks (n, H, W), ncontours (n,), dots (mapH, mapW, 16) u16)"""
+    n, H, W = frames.shape
+    ar = np.arange(16, dtype=np.uint8)
+    if background is None:
+        d0 = np.zeros((mapH, mapW, 16), np.uint16)
+        for f in range(n):
+            x, y = int(pos[f][0]), int(pos[f][1])
+            d0[y:y + H, x:x + W] += (frames[f][:, :, None] == ar).astype(np.uint16)
+        best = d0.max(axis=2)
+        background = np.where(best != 0, d0.argmax(axis=2), 0).astype(np.uint8)
+    dots = np.zeros((mapH, mapW, 16), np.uint16)
+    masks = np.zeros((n, H, W), np.uint8)
+    nc = np.zeros(n, np.uint32)
+    for f in range(n):
+        x, y = int(pos[f][0]), int(pos[f][1])
+        m, cont = foreground(background, x, y, frames[f], medians[f])
+        masks[f] = m
+        nc[f] = len(cont)
+        dots[y:y + H, x:x + W] += ((frames[f][:, :, None] == ar) & (m[:, :, None] == 0)).astype(np.uint16)
+    return dict(background=background, masks=masks, ncontours=nc, dots=dots)

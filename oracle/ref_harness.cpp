@@ -14,6 +14,10 @@
 //   dump  <frames.bin> W H N <out.bin>      canonical dump of every intermediate (see below)
 //   bench <frames.bin> W H N <reg|frc> T R  time the reference on T host threads, R repeats
 //   mask  <bg.bin> bgW bgH px py <frame.bin> W H <out.bin>
+//   filter <frames.bin> W H N <out.bin> R   frc::collector::collect + complete, then fdf::filter
+//                                           (src/fdf.hpp:40-91) over the collected fragments: dumps every
+//                                           frame's foreground contours and fde::mask, the backgrounds and
+//                                           the filtered fragments' dots; R > 1 repeats fdf::filter for timing
 //
 // frames.bin = N*H*W bytes, row-major, values 0..15 (== nil::read_raw format, src/nil.hpp:24).
 
@@ -32,6 +36,7 @@
 #include <vector>
 
 #include "fde.hpp"
+#include "fdf.hpp"
 #include "frc.hpp"
 #include "nic.hpp"
 
@@ -323,6 +328,90 @@ int run_mask(int argc, char** argv) {
   return 0;
 }
 
+// ---- pass 2: fdf::filter ------------------------------------------------------------------
+struct native_codec {  // both faces of main.cpp's native_compression (src/main.cpp:112-125)
+  template<typename Alloc>
+  [[nodiscard]] icd::compressed_t operator()(sid::nat::aimg_t<Alloc> const& image) const {
+    return nic::compress(image);
+  }
+  [[nodiscard]] sid::nat::dimg_t operator()(icd::compressed_t const& c, mrl::dimensions_t const& dim) const {
+    return nic::decompress(c, dim);
+  }
+};
+
+int run_filter(int argc, char** argv) {
+  if (argc < 7) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  std::size_t R = argc > 7 ? std::atoll(argv[7]) : 1;
+  auto frames = read_file(argv[2], N * W * H);
+  mrl::dimensions_t const dim{W, H};
+
+  std::vector<fgm::fragment> fragments;
+  {
+    frc::collector collector{dim};
+    memory_feed feed{frames.data(), W, H, 0, N};
+    collector.collect(feed, native_codec{},
+                      [](fgm::fragment const&, frc::frame_type const&, frc::image_type const&,
+                         frc::grid_type const&) {});
+    auto list = collector.complete();
+    for (auto& f : list) fragments.push_back(std::move(f));
+  }
+
+  FILE* out = std::fopen(argv[6], "wb");
+  if (!out) return 2;
+  std::fwrite("RMF2", 1, 4, out);
+  put32(out, W); put32(out, H); put32(out, N);
+  put32(out, static_cast<std::uint32_t>(fragments.size()));
+
+  // backgrounds exactly as the 4-argument fdf::filter makes them (src/fdf.hpp:21-34,79-89)
+  auto backgrounds = fdf::details::get_background(fragments);
+  for (auto& b : backgrounds) {
+    put32(out, static_cast<std::uint32_t>(b.image_.width()));
+    put32(out, static_cast<std::uint32_t>(b.image_.height()));
+    puti32(out, b.zero_.x_); puti32(out, b.zero_.y_);
+    std::fwrite(b.image_.data(), 1, b.image_.size(), out);
+  }
+
+  double best = 1e30;
+  std::vector<fgm::fragment> filtered;
+  for (std::size_t rep = 0; rep < R; ++rep) {
+    bool const dump = rep == 0;
+    auto t0 = std::chrono::steady_clock::now();
+    filtered = fdf::filter(
+        fragments, backgrounds, dim, native_codec{},
+        [&](fgm::fragment const& result, std::size_t frag, sid::nat::dimg_t const& image, std::size_t no,
+            sid::nat::dimg_t const& median, fgm::point_t const& pos, fdf::contours_t const& foreground,
+            auto const& mask) {
+          if (!dump) return;
+          put32(out, static_cast<std::uint32_t>(frag));
+          put32(out, static_cast<std::uint32_t>(no));
+          puti32(out, pos.x_ - result.zero().x_);
+          puti32(out, pos.y_ - result.zero().y_);
+          put32(out, static_cast<std::uint32_t>(foreground.size()));
+          for (auto& c : foreground) {
+            auto& e = c.enclosure();
+            put32(out, c.area());
+            put32(out, static_cast<std::uint32_t>(e.left_)); put32(out, static_cast<std::uint32_t>(e.top_));
+            put32(out, static_cast<std::uint32_t>(e.right_)); put32(out, static_cast<std::uint32_t>(e.bottom_));
+            put32(out, static_cast<std::uint32_t>(value(c.color())));
+          }
+          std::fwrite(mask.data(), 1, W * H, out);
+        });
+    auto t1 = std::chrono::steady_clock::now();
+    best = std::min(best, std::chrono::duration<double>(t1 - t0).count());
+  }
+  for (auto& f : filtered) {
+    put32(out, static_cast<std::uint32_t>(f.dots().width()));
+    put32(out, static_cast<std::uint32_t>(f.dots().height()));
+    puti32(out, f.zero().x_); puti32(out, f.zero().y_);
+    std::fwrite(f.dots().data(), sizeof(fgm::dot_type), f.dots().size(), out);
+  }
+  std::fclose(out);
+  std::printf("{\"mode\": \"filter\", \"frames\": %zu, \"fragments\": %zu, \"reps\": %zu, \"best_s\": %.6f, "
+              "\"fps_best\": %.3f}\n", N, fragments.size(), R, best, N / best);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -331,5 +420,6 @@ int main(int argc, char** argv) {
   if (mode == "dump") return run_dump(argc, argv);
   if (mode == "bench") return run_bench(argc, argv);
   if (mode == "mask") return run_mask(argc, argv);
+  if (mode == "filter") return run_filter(argc, argv);
   return 1;
 }

@@ -112,3 +112,53 @@ def ref_mask(bg: np.ndarray, px: int, py: int, frame: np.ndarray) -> np.ndarray:
         np.ascontiguousarray(frame, np.uint8).tofile(ff)
         subprocess.check_call([REF_BIN, "mask", fb, str(bw), str(bh), str(px), str(py), ff, str(W), str(H), fo])
         return np.fromfile(fo, np.uint8).reshape(H, W)
+
+
+CONTOUR_DTYPE = np.dtype([("area", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"),
+                          ("colour", "<u4")])
+
+
+def parse_filter_dump(buf: bytes) -> dict:
+    """Dump of `ref_harness filter`: the reference's frc::collector fragments run through fdf::filter."""
+    assert buf[:4] == b"RMF2"
+    W, H, N, nfrag = struct.unpack_from("<IIII", buf, 4)
+    pos = 20
+    backgrounds = []
+    for _ in range(nfrag):
+        bw, bh, zx, zy = struct.unpack_from("<IIii", buf, pos)
+        pos += 16
+        img = np.frombuffer(buf, np.uint8, bw * bh, pos).reshape(bh, bw).copy()
+        pos += bw * bh
+        backgrounds.append(dict(image=img, zero=(zx, zy)))
+    frames = []
+    for _ in range(N):
+        frag, no, x, y, nc = struct.unpack_from("<IIiiI", buf, pos)
+        pos += 20
+        cont = np.frombuffer(buf, CONTOUR_DTYPE, nc, pos).copy()
+        pos += nc * CONTOUR_DTYPE.itemsize
+        mask = np.frombuffer(buf, np.uint8, W * H, pos).reshape(H, W).copy()
+        pos += W * H
+        frames.append(dict(fragment=frag, number=no, x=x, y=y, contours=cont, mask=mask))
+    fragments = []
+    for _ in range(nfrag):
+        bw, bh, zx, zy = struct.unpack_from("<IIii", buf, pos)
+        pos += 16
+        dots = np.frombuffer(buf, "<u2", bw * bh * 16, pos).reshape(bh, bw, 16).copy()
+        pos += bw * bh * 32
+        fragments.append(dict(dots=dots, zero=(zx, zy)))
+    assert pos == len(buf), (pos, len(buf))
+    return dict(W=W, H=H, N=N, backgrounds=backgrounds, frames=frames, fragments=fragments)
+
+
+def ref_filter(frames: np.ndarray, reps: int = 1) -> dict:
+    """frames (N, H, W) -> the real reference's collect + fdf::filter results (+ 'timing')."""
+    assert have_ref()
+    N, H, W = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "frames.bin"), os.path.join(td, "dump.bin")
+        np.ascontiguousarray(frames, np.uint8).tofile(fin)
+        out = subprocess.check_output([REF_BIN, "filter", fin, str(W), str(H), str(N), fout, str(reps)])
+        with open(fout, "rb") as f:
+            d = parse_filter_dump(f.read())
+    d["timing"] = json.loads(out.decode().strip().splitlines()[-1])
+    return d

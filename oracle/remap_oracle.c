@@ -448,6 +448,107 @@ void ro_foreground_mask(const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t p
       mask[(size_t)y * W + x] = bg[idx + (ptrdiff_t)y * bgW + x] == frame[(size_t)y * W + x] ? 0xFF : 0x00;
 }
 
+/* ---- f2: pass-2 foreground extraction: fde::extractor::extract + fde::mask (src/fde.hpp:83-146) over
+ * cte::extractor (src/cte.hpp:60-166) and ctr::contour (src/ctr.hpp:121-235) -------------------------
+ *
+ * What the reference does per frame (src/fdf.hpp:58-66):
+ *   1. generate_mask: eq[p] = background window == frame (src/fde.hpp:87,106-114);
+ *   2. cte::extractor::extract(median, pred = eq[p] == 0): scan the INTERIOR pixels (rows 1..H-2, columns
+ *      1..W-2, src/cte.hpp:66-72,92) in row-major order; a pixel that has no contour id yet and satisfies
+ *      the predicate starts a breadth-first fill over 4-connected pixels of EQUAL MEDIAN colour
+ *      (push_pixel, src/cte.hpp:143-157).  Row 0, columns 0 and W-1 and the LAST TWO rows (H-2 and H-1) are
+ *      pre-marked with the horizon id (clear_outline, src/cte.hpp:159-177: the side-column loop stops at row
+ *      H-3 and the closing loop marks everything from row H-2 on) and are never entered or seeded;
+ *   3. contours whose area (pixel count, ctr::contour::add_point src/ctr.hpp:139-149) exceeds
+ *      frame area / 5 are dropped (src/fde.hpp:94-100);
+ *   4. fde::mask paints every kept contour's pixels (contour::recover fills each horizontal run between
+ *      its left-edge and right-edge pixel, src/ctr.hpp:151-170) and then every kept contour's enclosure
+ *      with EXCLUSIVE right and bottom bounds (src/fde.hpp:133-143; enclosure = min/max column of the
+ *      edge pixels, first/last edge row, src/ctr.hpp:96-107).
+ * The fill order inside a contour does not influence any of this, so the restatement uses a stack.
+ * Contours come out in the reference's order (first seed in row-major order).  The reference's contour
+ * ids are uint16 (src/cte.hpp:20,96-98) and wrap after 65,534 contours in one frame; that case is outside
+ * the contract (returns (size_t)-1). */
+typedef struct { uint32_t area, left, top, right, bottom, colour; } ro_contour;
+
+static int ro_u32_cmp(const void* a, const void* b) {
+  const uint32_t x = *(const uint32_t*)a, y = *(const uint32_t*)b;
+  return x < y ? -1 : x > y;
+}
+
+size_t ro_foreground(const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, int32_t py, const uint8_t* frame,
+                     const uint8_t* median, uint32_t W, uint32_t H, uint8_t* out_mask, ro_contour* contours,
+                     size_t cap) {
+  (void)bgH;
+  const size_t npx = (size_t)W * H;
+  const ptrdiff_t idx = (ptrdiff_t)bgW * py + px;
+  uint32_t* id = (uint32_t*)calloc(npx, sizeof(uint32_t));
+  uint32_t* stack = (uint32_t*)malloc(npx * sizeof(uint32_t));
+  uint32_t* members = (uint32_t*)malloc(npx * sizeof(uint32_t)); /* pixels of the contour being filled */
+  const uint32_t area_limit = (uint32_t)(npx / 5);                /* src/fde.hpp:94 */
+  size_t ncont = 0, nkept = 0;
+  memset(out_mask, 0, npx);
+  if (W < 3 || H < 4) { free(id); free(stack); free(members); return 0; }
+  /* kept contours are remembered so that the enclosure pass runs after ALL pixel passes (src/fde.hpp:129-143) */
+  ro_contour* kept = (ro_contour*)malloc((npx + 1) * sizeof(ro_contour));
+  size_t kept_cap = npx + 1;
+  for (uint32_t y = 1; y + 2 < H; ++y) { /* row H-2 is scanned by the reference but is all horizon */
+    for (uint32_t x = 1; x + 1 < W; ++x) {
+      const size_t p = (size_t)y * W + x;
+      if (id[p] != 0) continue;
+      if (bg[idx + (ptrdiff_t)y * bgW + x] == frame[p]) continue; /* pred: mask value == 0 <=> differs */
+      if (++ncont >= 65535) { free(id); free(stack); free(members); free(kept); return (size_t)-1; }
+      const uint8_t colour = median[p];
+      ro_contour c = {0, 0, 0, 0, 0, colour};
+      size_t sp = 0, nm = 0;
+      stack[sp++] = (uint32_t)p;
+      id[p] = (uint32_t)ncont;
+      while (sp) {
+        const uint32_t q = stack[--sp];
+        members[nm++] = q;
+        ++c.area;
+        const int32_t nb[4] = {-1, 1, -(int32_t)W, (int32_t)W};
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t r = (uint32_t)((int32_t)q + nb[k]);
+          const uint32_t rx = r % W, ry = r / W;
+          if (rx == 0 || ry == 0 || rx == W - 1 || ry >= H - 2) continue; /* horizon */
+          if (median[r] != colour || id[r] != 0) continue;
+          id[r] = (uint32_t)ncont;
+          stack[sp++] = r;
+        }
+      }
+      /* enclosure (src/ctr.hpp:96-107, cdt::limits::update src/cdt.hpp:183-190): over the pixels that carry
+       * a left or right edge (a horizontal neighbour of another colour, or the horizon), in ascending
+       * position order; note the `else if` -- a value that raises the upper bound never lowers the lower
+       * one, and the lower bound starts at SIZE_MAX (here: UINT32_MAX, which also makes the fill empty). */
+      qsort(members, nm, sizeof(uint32_t), ro_u32_cmp);
+      {
+        uint32_t lower = UINT32_MAX, upper = 0, first = UINT32_MAX, last = 0;
+        for (size_t k = 0; k < nm; ++k) {
+          const uint32_t q = members[k], qx = q % W;
+          const int le = qx == 1 || median[q - 1] != colour, re = qx == W - 2 || median[q + 1] != colour;
+          if (!le && !re) continue;
+          if (first == UINT32_MAX) first = q;
+          last = q;
+          if (qx > upper) upper = qx; else if (qx < lower) lower = qx;
+        }
+        c.left = lower; c.right = upper; c.top = first / W; c.bottom = last / W;
+      }
+      if (c.area > area_limit) continue;
+      for (size_t k = 0; k < nm; ++k) out_mask[members[k]] = 1;
+      if (nkept < kept_cap) kept[nkept] = c;
+      if (contours && nkept < cap) contours[nkept] = c;
+      ++nkept;
+    }
+  }
+  for (size_t k = 0; k < nkept && k < kept_cap; ++k)
+    for (uint32_t y = kept[k].top; y < kept[k].bottom; ++y)
+      for (uint32_t x = kept[k].left; x < kept[k].right; ++x) out_mask[(size_t)y * W + x] = 1;
+  free(id); free(stack); free(members); free(kept);
+  return nkept;
+}
+size_t ro_sizeof_contour(void) { return sizeof(ro_contour); }
+
 size_t ro_sizeof_keypoint(void) { return sizeof(ro_keypoint); }
 size_t ro_sizeof_region_vote(void) { return sizeof(ro_region_vote); }
 size_t ro_sizeof_match_result(void) { return sizeof(ro_match_result); }

@@ -175,6 +175,34 @@ class Registrar:
                                             image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
         return dots, image, mask
 
+    def filter_fragment(self, placements, map_w, map_h, background=None, want_dots=True, want_fgmasks=False):
+        """fdf::filter for one fragment (src/fdf.hpp:40-75): per placed frame the pass-2 foreground mask
+        (fde::extractor::extract + fde::mask on the frame's median image), then the masked blit and blend.
+        background: (map_h, map_w) uint8 or None (= blend of the plain blit of the placements).
+        -> dict(dots|None, image, mask, fgmasks (n, H, W)|None, ncontours (n,), times_ms, frames_deferred)"""
+        pl = np.ascontiguousarray(placements, PLACEMENT_DTYPE)
+        n = len(pl)
+        dots = np.zeros((map_h, map_w, 16), np.uint16) if want_dots else None
+        image = np.zeros((map_h, map_w), np.uint8)
+        mask = np.zeros((map_h, map_w), np.uint8)
+        fg = np.zeros((n, self.height, self.width), np.uint8) if want_fgmasks else None
+        nc = np.zeros(n, np.uint32)
+        bg = None
+        if background is not None:
+            bg = np.ascontiguousarray(background, np.uint8)
+            assert bg.shape == (map_h, map_w)
+        vp = C.c_void_p
+        self._check(self._lib.rb_filter_fragment(
+            self._ctx, pl.ctypes.data_as(vp), n, map_w, map_h, bg.ctypes.data_as(vp) if bg is not None else None,
+            dots.ctypes.data_as(vp) if want_dots else None, image.ctypes.data_as(vp), mask.ctypes.data_as(vp),
+            fg.ctypes.data_as(vp) if want_fgmasks else None, nc.ctypes.data_as(vp)))
+        ms = (C.c_float * 3)()
+        deferred = C.c_uint32()
+        self._check(self._lib.rb_filter_times(self._ctx, ms, 3, C.byref(deferred)))
+        return dict(dots=dots, image=image, mask=mask, fgmasks=fg, ncontours=nc,
+                    times_ms=dict(background=ms[0], foreground=ms[1], masked_blit=ms[2]),
+                    frames_deferred=int(deferred.value))
+
     # -- introspection ------------------------------------------------------------------------
     @property
     def stream(self):

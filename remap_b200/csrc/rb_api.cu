@@ -19,6 +19,7 @@
 #include "rb_kpm_fast.cuh"
 #include "rb_prep.cuh"
 #include "rb_blit.cuh"
+#include "rb_fg.cuh"
 
 static_assert(sizeof(rb_region_vote) == sizeof(RbRegionVote), "ABI mirror of RbRegionVote");
 static_assert(sizeof(rb_bin) == sizeof(RbBin), "ABI mirror of RbBin");
@@ -332,6 +333,21 @@ struct rb_ctx {
   uint8_t* d_bg;       // scratch for rb_foreground_mask
   size_t bg_cap;
   uint8_t* d_fgframe;  // dense frame scratch
+  // pass-2 filter (rb_filter_fragment)
+  bool fg_ready, fg_fast_ok;
+  uint32_t fg_NW, fg_rcap, fg_scap, fg_grid, fg_gen_rcap, fg_gen_grid;
+  size_t fg_smem, fg_gen_smem, fg_slab;
+  uint32_t* d_fgbits;      // [placement][H][NW]
+  uint32_t* d_fg_nkept;    // [placement]
+  uint32_t* d_fg_deferred; // [placement]
+  uint32_t* d_fg_count;    // [0] frames deferred by the shared-memory variant
+  size_t fg_cap;           // placements the three arrays above hold
+  uint8_t* d_fg_scratch;   // slabs of the general variant
+  uint8_t* d_fg_bytes;     // parity tap: masks as bytes, one chunk
+  cudaEvent_t fg_ev[4];
+  float fg_ms[3];
+  uint32_t fg_last_deferred;
+  size_t med_lo, med_hi;   // frames whose medians K1 has written
   uint8_t* d_mask;     // dense mask [H][W]
   size_t bytes;
   uint32_t code_slots, off_slots, tile_pitch, tile_rows;
@@ -598,6 +614,10 @@ void rb_destroy(rb_ctx* c) {
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_places); cudaFree(c->d_map); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
+  cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred); cudaFree(c->d_fg_count); cudaFree(c->d_fg_scratch);
+  cudaFree(c->d_fg_bytes);
+  for (int i = 0; i < 4; ++i)
+    if (c->fg_ev[i]) cudaEventDestroy(c->fg_ev[i]);
   for (int b = 0; b < RB_MAX_BATCHES; ++b) {
     for (int i = 0; i < 7; ++i)
       if (c->bev[b].e[i]) cudaEventDestroy(c->bev[b].e[i]);
@@ -884,6 +904,11 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
   if (rc != RB_OK) return rc;
   c->reg_first = first;
   c->reg_n = n;
+  if (c->med_hi == c->med_lo) { c->med_lo = first; c->med_hi = first + n; }
+  else {  // the frames in between keep whatever an earlier call wrote; callers register contiguous ranges
+    if (first < c->med_lo) c->med_lo = first;
+    if (first + n > c->med_hi) c->med_hi = first + n;
+  }
   return RB_OK;
 }
 
@@ -939,6 +964,11 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   }
   c->reg_first = first;
   c->reg_n = n;
+  if (c->med_hi == c->med_lo) { c->med_lo = first; c->med_hi = first + n; }
+  else {  // the frames in between keep whatever an earlier call wrote; callers register contiguous ranges
+    if (first < c->med_lo) c->med_lo = first;
+    if (first + n > c->med_hi) c->med_hi = first + n;
+  }
   return RB_OK;
 }
 
@@ -1091,8 +1121,8 @@ int rb_blit_blend(rb_ctx* c, const rb_placement* placements, size_t n, uint32_t 
   uint8_t* d_msk = d_img + px;
   if (n) RB_CUDA(c, cudaMemcpyAsync(c->d_places, placements, n * sizeof(RbPlacement), cudaMemcpyHostToDevice, c->stream));
   const dim3 grid((mapW + RB_BLIT_TX - 1) / RB_BLIT_TX, (mapH + RB_BLIT_TY - 1) / RB_BLIT_TY);
-  rb_blit_blend_kernel<<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places, (uint32_t)n,
-                                                           mapW, mapH, d_dots, d_img, d_msk);
+  rb_blit_blend_kernel<false><<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places,
+                                                                  (uint32_t)n, mapW, mapH, d_dots, d_img, d_msk, nullptr, 0);
   RB_LAUNCHED(c, "rb_blit_blend_kernel");
   if (out_dots) RB_CUDA(c, cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream));
   if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
@@ -1142,6 +1172,187 @@ int rb_foreground_mask_resident(rb_ctx* c, const uint8_t* bg, uint32_t bgW, uint
   if (frame >= c->uploaded) { c->err = "rb_foreground_mask_resident: frame not uploaded"; return RB_ERR_STATE; }
   RB_CUDA(c, cudaSetDevice(c->device));
   return fgmask_common(c, bg, bgW, bgH, px, py, c->d_frames + c->g.frame_stride * frame, c->g.pitch, out_mask);
+}
+
+// ---- pass 2: fdf::filter for one fragment (src/fdf.hpp:40-75) ---------------------------------------
+static int fg_setup(rb_ctx* c) {
+  if (c->fg_ready) return RB_OK;
+  const RbGeom& g = c->g;
+  if (g.H < 4 || g.W < 3) { c->err = "rb_filter_fragment: frame too small"; return RB_ERR_INVALID; }
+  c->fg_NW = (g.W + 31) / 32;
+  int smem_max = 0, smem_sm = 0, smem_res = 0;
+  RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  RB_CUDA(c, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+  RB_CUDA(c, cudaDeviceGetAttribute(&smem_res, cudaDevAttrReservedSharedMemoryPerBlock, c->device));
+  const size_t fixed = (rbg::fixed_bytes(g.H, c->fg_NW) + 15) & ~(size_t)15;
+  const uint32_t rmax = (g.W - 2) * (g.H - 3);  // every interior pixel its own run
+  int want = getenv("RB_FG_CTAS") ? atoi(getenv("RB_FG_CTAS")) : 2;
+  if (want < 1) want = 1;
+  if (want > 4) want = 4;
+  // shared-memory variant: `want` CTAs per SM share the SM's shared memory; a quarter of the table space goes
+  // to the statistics slots, the rest to the labels
+  size_t budget = (size_t)smem_sm / want - smem_res;
+  if (budget > (size_t)smem_max) budget = smem_max;
+  c->fg_fast_ok = false;
+  if (budget > fixed + 8192) {
+    const size_t avail = budget - fixed - 64;
+    uint32_t scap = (uint32_t)(avail / 4 / 16);
+    if (scap > 4096) scap = 4096;
+    size_t r = (avail - (size_t)scap * 16) * 8 / 17;  // 2 bytes label + 1 bit per run
+    if (r > rmax) r = rmax;
+    if (r + scap > 65535) r = 65535 - scap;
+    r &= ~(size_t)31;
+    if (getenv("RB_FG_RCAP")) r = (size_t)atoi(getenv("RB_FG_RCAP"));  // tests: force deferrals
+    if (getenv("RB_FG_SCAP")) scap = (uint32_t)atoi(getenv("RB_FG_SCAP"));
+    c->fg_rcap = (uint32_t)r;
+    c->fg_scap = scap;
+    c->fg_smem = fixed + rbg::table_bytes<uint16_t>(c->fg_rcap, c->fg_scap);
+    if (c->fg_rcap >= 64 && scap >= 1 && c->fg_smem <= (size_t)smem_max && c->fg_rcap + scap <= 65535) {
+      RB_CUDA(c, cudaFuncSetAttribute(rb_fg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fg_smem));
+      int occ = 0;
+      RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_fg_kernel, RB_FG_NT, c->fg_smem));
+      if (occ >= 1) { c->fg_fast_ok = true; c->fg_grid = (uint32_t)(occ * c->sm_count); }
+    }
+  }
+  if (getenv("RB_FG_GENERAL_ONLY")) c->fg_fast_ok = false;
+  // general variant: bit maps in shared memory, worst-case tables in a global slab per CTA
+  c->fg_gen_rcap = rmax;
+  c->fg_gen_smem = fixed;
+  if (c->fg_gen_smem > (size_t)smem_max) { c->err = "rb_filter_fragment: frame bit maps exceed shared memory"; return RB_ERR_INVALID; }
+  RB_CUDA(c, cudaFuncSetAttribute(rb_fg_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fg_gen_smem));
+  int occ = 0;
+  RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_fg_general_kernel, RB_FG_NT, c->fg_gen_smem));
+  if (occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  c->fg_gen_grid = (uint32_t)(occ * c->sm_count);
+  c->fg_slab = (rbg::table_bytes<uint32_t>(rmax, rmax) + 255) & ~(size_t)255;
+  RB_CUDA(c, dmalloc(c, &c->d_fg_scratch, c->fg_slab * c->fg_gen_grid));
+  RB_CUDA(c, dmalloc(c, &c->d_fg_count, 256));
+  for (int i = 0; i < 4; ++i) RB_CUDA(c, cudaEventCreate(&c->fg_ev[i]));
+  c->fg_ready = true;
+  return RB_OK;
+}
+
+int rb_filter_fragment(rb_ctx* c, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH,
+                       const uint8_t* background, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask,
+                       uint8_t* out_fgmasks, uint32_t* out_ncontours) {
+  if (!c || (!placements && n) || mapW == 0 || mapH == 0 || n > 0xFFFFFFFFu) return RB_ERR_INVALID;
+  if (!c->d_median) { c->err = "rb_filter_fragment: context created with compute_median = 0"; return RB_ERR_STATE; }
+  const RbGeom& g = c->g;
+  for (size_t i = 0; i < n; ++i) {
+    const rb_placement& p = placements[i];
+    if (p.frame >= c->uploaded || p.frame < c->med_lo || p.frame >= c->med_hi) {
+      c->err = "rb_filter_fragment: frame not registered (its median image is needed, src/fdf.hpp:60)";
+      return RB_ERR_STATE;
+    }
+    if (p.x < 0 || p.y < 0 || (uint64_t)p.x + g.W > mapW || (uint64_t)p.y + g.H > mapH) {
+      c->err = "rb_filter_fragment: a frame lies outside the map";
+      return RB_ERR_INVALID;
+    }
+  }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  int rc = fg_setup(c);
+  if (rc != RB_OK) return rc;
+  if (n > c->places_cap) {
+    if (c->d_places) { cudaFree(c->d_places); c->bytes -= c->places_cap * sizeof(RbPlacement); c->d_places = nullptr; }
+    c->places_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_places, n * sizeof(RbPlacement)));
+    c->places_cap = n;
+  }
+  const size_t px = (size_t)mapW * mapH, need = px * 34 + 256;
+  if (need > c->map_cap) {
+    if (c->d_map) { cudaFree(c->d_map); c->bytes -= c->map_cap; c->d_map = nullptr; }
+    c->map_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_map, need));
+    c->map_cap = need;
+  }
+  if (px + 64 > c->bg_cap) {
+    if (c->d_bg) { cudaFree(c->d_bg); c->bytes -= c->bg_cap; c->d_bg = nullptr; c->bg_cap = 0; }
+    RB_CUDA(c, dmalloc(c, &c->d_bg, px + 64));
+    c->bg_cap = px + 64;
+  }
+  const size_t fwords = (size_t)g.H * c->fg_NW;
+  if (n > c->fg_cap) {
+    cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred);
+    c->bytes -= c->fg_cap * (fwords * 4 + 8);
+    c->d_fgbits = c->d_fg_nkept = c->d_fg_deferred = nullptr;
+    c->fg_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_fgbits, n * fwords * 4));
+    RB_CUDA(c, dmalloc(c, &c->d_fg_nkept, n * 4));
+    RB_CUDA(c, dmalloc(c, &c->d_fg_deferred, n * 4));
+    c->fg_cap = n;
+  }
+  uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
+  uint8_t* d_img = c->d_map + px * 32;
+  uint8_t* d_msk = d_img + px;
+  const dim3 grid((mapW + RB_BLIT_TX - 1) / RB_BLIT_TX, (mapH + RB_BLIT_TY - 1) / RB_BLIT_TY);
+  if (n) RB_CUDA(c, cudaMemcpyAsync(c->d_places, placements, n * sizeof(RbPlacement), cudaMemcpyHostToDevice, c->stream));
+  RB_CUDA(c, cudaEventRecord(c->fg_ev[0], c->stream));
+  // 1. the background: given, or fragment.blend() of the plain blit (fdf::details::get_background, src/fdf.hpp:21-34)
+  if (background) {
+    RB_CUDA(c, cudaMemcpyAsync(c->d_bg, background, px, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    rb_blit_blend_kernel<false><<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places,
+                                                                    (uint32_t)n, mapW, mapH, nullptr, d_img, nullptr, nullptr, 0);
+    RB_LAUNCHED(c, "rb_blit_blend_kernel");
+    RB_CUDA(c, cudaMemcpyAsync(c->d_bg, d_img, px, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  RB_CUDA(c, cudaEventRecord(c->fg_ev[1], c->stream));
+  // 2. every frame's foreground bit map (fde::extractor::extract + fde::mask, src/fdf.hpp:62-63)
+  RB_CUDA(c, cudaMemsetAsync(c->d_fg_count, 0, 8, c->stream));
+  if (n) {
+    RbFgParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = g;
+    p.frames = c->d_frames; p.median = c->d_median; p.bg = c->d_bg; p.bgW = mapW; p.bgH = mapH;
+    p.places = c->d_places; p.n = (uint32_t)n; p.NW = c->fg_NW;
+    p.area_limit = (uint32_t)(((uint64_t)g.W * g.H) / 5);
+    p.fgbits = c->d_fgbits; p.nkept = c->d_fg_nkept; p.deferred = c->d_fg_deferred; p.ndeferred = c->d_fg_count;
+    if (c->fg_fast_ok) {
+      p.rcap = c->fg_rcap; p.scap = c->fg_scap;
+      const uint32_t blocks = n < c->fg_grid ? (uint32_t)n : c->fg_grid;
+      rb_fg_kernel<<<blocks, RB_FG_NT, c->fg_smem, c->stream>>>(p);
+      RB_LAUNCHED(c, "rb_fg_kernel");
+      p.todo = c->d_fg_deferred; p.ntodo = c->d_fg_count;
+    }
+    p.rcap = c->fg_gen_rcap; p.scap = c->fg_gen_rcap;
+    p.scratch = c->d_fg_scratch; p.scratch_stride = c->fg_slab;
+    const uint32_t blocks = n < c->fg_gen_grid ? (uint32_t)n : c->fg_gen_grid;
+    rb_fg_general_kernel<<<blocks, RB_FG_NT, c->fg_gen_smem, c->stream>>>(p);
+    RB_LAUNCHED(c, "rb_fg_general_kernel");
+  }
+  RB_CUDA(c, cudaEventRecord(c->fg_ev[2], c->stream));
+  // 3. the masked blit of every frame + blend of the result (src/fdf.hpp:64, src/fgm.hpp:71-85,115-135)
+  rb_blit_blend_kernel<true><<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places,
+                                                                 (uint32_t)n, mapW, mapH, d_dots, d_img, d_msk, c->d_fgbits, c->fg_NW);
+  RB_LAUNCHED(c, "rb_blit_blend_kernel");
+  RB_CUDA(c, cudaEventRecord(c->fg_ev[3], c->stream));
+  if (out_dots) RB_CUDA(c, cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
+  if (out_mask) RB_CUDA(c, cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream));
+  if (out_ncontours && n) RB_CUDA(c, cudaMemcpyAsync(out_ncontours, c->d_fg_nkept, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaMemcpyAsync(&c->fg_last_deferred, c->d_fg_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  if (out_fgmasks && n) {  // parity tap: bit maps -> bytes, in chunks through a small scratch buffer
+    const size_t chunk = 256, fbytes = (size_t)g.W * g.H;
+    if (!c->d_fg_bytes) RB_CUDA(c, dmalloc(c, &c->d_fg_bytes, chunk * fbytes));
+    for (size_t f0 = 0; f0 < n; f0 += chunk) {
+      const size_t m = n - f0 < chunk ? n - f0 : chunk;
+      rb_fgbits_bytes_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_fgbits + f0 * fwords, (uint32_t)m, g.W, g.H, c->fg_NW,
+                                                                      c->d_fg_bytes);
+      RB_LAUNCHED(c, "rb_fgbits_bytes_kernel");
+      RB_CUDA(c, cudaMemcpyAsync(out_fgmasks + f0 * fbytes, c->d_fg_bytes, m * fbytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 3; ++i) RB_CUDA(c, cudaEventElapsedTime(&c->fg_ms[i], c->fg_ev[i], c->fg_ev[i + 1]));
+  return RB_OK;
+}
+
+int rb_filter_times(rb_ctx* c, float* ms, size_t n, uint32_t* frames_deferred) {
+  if (!c || !c->fg_ready) return RB_ERR_STATE;
+  for (size_t i = 0; i < n && i < 3; ++i) ms[i] = c->fg_ms[i];
+  if (frames_deferred) *frames_deferred = c->fg_last_deferred;
+  return RB_OK;
 }
 
 }  // extern "C"

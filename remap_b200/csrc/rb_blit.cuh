@@ -28,13 +28,18 @@ struct RbPlacement {
 #define RB_BLIT_NT (RB_BLIT_TX * RB_BLIT_TY)
 #define RB_BLIT_CHUNK 1024
 
+// MASKED = true is fdf::filter's blit (src/fdf.hpp:64, src/fgm.hpp:71-85): a frame pixel counts only where the
+// frame's foreground mask is 0; fgbits = [placement][H][NW] bit maps written by rb_fg.cuh (bit set = foreground).
+template <bool MASKED>
 __global__ void __launch_bounds__(RB_BLIT_NT) rb_blit_blend_kernel(const uint8_t* __restrict__ frames, uint32_t pitch,
                                                                    uint64_t frame_stride, uint32_t W, uint32_t H,
                                                                    const RbPlacement* __restrict__ places, uint32_t n,
                                                                    uint32_t mapW, uint32_t mapH, uint16_t* __restrict__ dots,
-                                                                   uint8_t* __restrict__ image, uint8_t* __restrict__ mask) {
+                                                                   uint8_t* __restrict__ image, uint8_t* __restrict__ mask,
+                                                                   const uint32_t* __restrict__ fgbits, uint32_t NW) {
   __shared__ uint16_t hist[16][RB_BLIT_NT];
   __shared__ RbPlacement hit[RB_BLIT_CHUNK];
+  __shared__ uint32_t hit_idx[MASKED ? RB_BLIT_CHUNK : 1];
   __shared__ uint32_t nhit;
   const uint32_t tid = threadIdx.x;
   const uint32_t tx0 = blockIdx.x * RB_BLIT_TX, ty0 = blockIdx.y * RB_BLIT_TY;
@@ -49,14 +54,20 @@ __global__ void __launch_bounds__(RB_BLIT_NT) rb_blit_blend_kernel(const uint8_t
       const RbPlacement p = places[i];
       const bool over = p.x < (int32_t)(tx0 + RB_BLIT_TX) && p.x + (int32_t)W > (int32_t)tx0 &&
                         p.y < (int32_t)(ty0 + RB_BLIT_TY) && p.y + (int32_t)H > (int32_t)ty0;
-      if (over) hit[atomicAdd(&nhit, 1u)] = p;  // order does not matter: the increments commute
+      if (over) {  // order does not matter: the increments commute
+        const uint32_t at = atomicAdd(&nhit, 1u);
+        hit[at] = p;
+        if (MASKED) hit_idx[at] = i;
+      }
     }
     __syncthreads();
     const uint32_t nh = nhit;
     for (uint32_t j = 0; j < nh; ++j) {
       const RbPlacement p = hit[j];
       const uint32_t fx = mx - (uint32_t)p.x, fy = my - (uint32_t)p.y;  // unsigned: negative wraps far above W / H
-      if (fx < W && fy < H) {
+      bool take = fx < W && fy < H;
+      if (MASKED && take) take = !((__ldg(fgbits + ((uint64_t)hit_idx[j] * H + fy) * NW + (fx >> 5)) >> (fx & 31)) & 1u);
+      if (take) {
         const uint32_t c = frames[(uint64_t)p.frame * frame_stride + (uint64_t)fy * pitch + fx] & 15u;
         ++hist[c][tid];  // uint16: wraps at 65,536 like fgm::dot_type (src/fgm.hpp:14,94)
       }

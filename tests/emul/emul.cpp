@@ -15,6 +15,7 @@
 #include "../../remap_b200/csrc/rb_host.hpp"
 #include "../../remap_b200/csrc/rb_kpe.cuh"
 #include "../../remap_b200/csrc/rb_prep.cuh"
+#include "../../remap_b200/csrc/rb_fg.cuh"
 
 extern "C" {
 
@@ -131,6 +132,54 @@ int emul_register(const uint8_t* frames, uint32_t n, uint32_t W, uint32_t H, uin
     rbm::declare_pair(g, votes + (size_t)pair * g.nreg, results + pair);
   }
   return 0;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// Pass-2 foreground (rb_fg.cuh): the phases of rbg::frame_body run thread by thread.  frames / medians:
+// n*H*W bytes (dense), bg: bgH*bgW, places: n x (frame, x, y).  general = 0: 16-bit labels, tables of
+// nplaces x (frame, x, y) placements; (rcap, scap) entries, returns the number of frames that did not fit (their bits are left untouched);
+// general = 1: 32-bit labels, worst-case tables.  bits: n*H*NW words, nkept: n.
+int emul_fg(const uint8_t* frames, const uint8_t* medians, uint32_t n, uint32_t W, uint32_t H, const uint8_t* bg, uint32_t bgW,
+            uint32_t bgH, const int32_t* places, uint32_t nplaces, int general, uint32_t rcap, uint32_t scap, uint32_t* bits, uint32_t* nkept) {
+  RbFgParams p;
+  memset(&p, 0, sizeof(p));
+  if (rb_make_geom(W, H, 4, 2, 16, 10, 3, &p.g) != 0) return -1;
+  const RbGeom& g = p.g;
+  std::vector<uint8_t> dfr((size_t)g.frame_stride * n + 256, 0x0E), dmed((size_t)g.median_stride * n + 256, 0x0D);
+  for (uint32_t f = 0; f < n; ++f)
+    for (uint32_t y = 0; y < H; ++y) {
+      memcpy(&dfr[f * g.frame_stride + (size_t)y * g.pitch], frames + ((size_t)f * H + y) * W, W);
+      memcpy(&dmed[f * g.median_stride + (size_t)y * g.mpitch + 2], medians + ((size_t)f * H + y) * W, W);
+    }
+  std::vector<uint8_t> dbg((size_t)bgW * bgH + 64, 0x0C);
+  memcpy(dbg.data(), bg, (size_t)bgW * bgH);
+  std::vector<RbPlacement> pl(nplaces);
+  for (uint32_t i = 0; i < nplaces; ++i) { pl[i].frame = (uint32_t)places[3 * i]; pl[i].x = places[3 * i + 1]; pl[i].y = places[3 * i + 2]; }
+  p.frames = dfr.data(); p.median = dmed.data(); p.bg = dbg.data(); p.bgW = bgW; p.bgH = bgH;
+  p.places = pl.data(); p.n = nplaces; p.NW = (W + 31) / 32;
+  p.area_limit = (uint32_t)(((uint64_t)W * H) / 5);
+  p.fgbits = bits; p.nkept = nkept;
+  const uint32_t rmax = (W - 2) * (H - 3);
+  p.rcap = general ? rmax : rcap;
+  p.scap = general ? rmax : scap;
+  const size_t fixed = (rbg::fixed_bytes(H, p.NW) + 15) & ~(size_t)15;
+  int deferred = 0;
+  if (general) {
+    std::vector<uint8_t> mem(fixed + rbg::table_bytes<uint32_t>(p.rcap, p.scap) + 64, 0xA5);
+    const RbFgWork<uint32_t> s = rbg::carve<uint32_t>(mem.data(), mem.data() + fixed, H, p.NW, p.rcap, p.scap);
+    for (uint32_t i = 0; i < nplaces; ++i)
+      if (!rbg::frame_body(p, s, i, RB_FG_NT)) ++deferred;
+  } else {
+    if (p.rcap + p.scap > 65535) return -2;
+    std::vector<uint8_t> mem(fixed + rbg::table_bytes<uint16_t>(p.rcap, p.scap) + 64, 0xA5);
+    const RbFgWork<uint16_t> s = rbg::carve<uint16_t>(mem.data(), mem.data() + fixed, H, p.NW, p.rcap, p.scap);
+    for (uint32_t i = 0; i < nplaces; ++i)
+      if (!rbg::frame_body(p, s, i, RB_FG_NT)) ++deferred;
+  }
+  return deferred;
 }
 
 }  // extern "C"

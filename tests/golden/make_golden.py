@@ -45,8 +45,42 @@ def cases():
     yield "repeat", synth.scrolling_tilemap(4, 160, 112, seed=19, world_w=512, world_h=256, n_tiles=3, speckle=0.02).frames
 
 
+def raw_filter_dump(frames):
+    N, H, W = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "f.bin"), os.path.join(td, "d.bin")
+        frames.tofile(fin)
+        subprocess.check_call([refdump.REF_BIN, "filter", fin, str(W), str(H), str(N), fout, "1"],
+                              stdout=subprocess.DEVNULL)
+        return np.fromfile(fout, np.uint8)
+
+
+def filter_cases():
+    """Pass 2 (fdf::filter, src/fdf.hpp:40-91) fixtures: the reference's own collect + filter."""
+    yield "filter_sprites", synth.scrolling_tilemap(8, 320, 224, seed=21, sprites=6, world_w=512, world_h=320).frames
+    yield "filter_small", synth.scrolling_tilemap(16, 160, 112, seed=22, sprites=4, world_w=320, world_h=256).frames
+    yield "filter_cuts", synth.scrolling_tilemap(14, 160, 112, seed=23, sprites=3, cut_every=5, levels=2,
+                                                 world_w=320, world_h=256).frames
+    rng = np.random.default_rng(24)   # a still camera and fresh noise every frame: many small contours
+    base = synth.scrolling_tilemap(1, 160, 112, seed=24, world_w=320, world_h=256).frames[0]
+    noisy = np.repeat(base[None], 10, axis=0).copy()
+    for f in range(10):
+        m = rng.random(base.shape) < 0.04
+        noisy[f][m] = rng.integers(0, 16, size=int(m.sum()), dtype=np.uint8)
+    yield "filter_noise", noisy
+
+
 def main():
     assert build_ref.build(), "needs /root/reference to build oracle/_ref"
+    for name, frames in filter_cases():
+        frames = np.ascontiguousarray(frames, np.uint8)
+        dump = raw_filter_dump(frames)
+        d = refdump.parse_filter_dump(dump.tobytes())
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), frames=frames, dump=dump)
+        print(name, frames.shape, "fragments", len(d["fragments"]), "contours/frame",
+              np.mean([len(f["contours"]) for f in d["frames"]]), "mask fraction", np.mean([f["mask"].mean() for f in d["frames"]]))
+    if "--filter-only" in sys.argv:
+        return
     for name, frames in cases():
         frames = np.ascontiguousarray(frames, np.uint8)
         dump = raw_dump(frames)

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.rb_abi_version() == 2
+    assert lib.rb_abi_version() == 3
 
 
 def test_default_config_is_the_reference_constants():

