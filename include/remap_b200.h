@@ -178,6 +178,10 @@ int rb_blit_blend(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_
 int rb_filter_fragment(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH,
                        const uint8_t* background, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask,
                        uint8_t* out_fgmasks, uint32_t* out_ncontours);
+/* Median images from the caller instead of from K1: n*H*W bytes into slots [first, first+n) of the median
+ * store.  fdf::filter reads the medians frc stored with every frame (src/fdf.hpp:60, src/frc.hpp:134); a
+ * caller that runs pass 2 in a context other than the one that registered the frames hands them over here. */
+int rb_upload_medians(rb_ctx* ctx, const uint8_t* medians, size_t first, size_t n);
 /* Last rb_filter_fragment: ms[0] background blit + blend, ms[1] foreground bit maps, ms[2] masked blit + blend;
  * frames_deferred = frames whose runs or contours did not fit the shared-memory tables and took the
  * global-memory variant of the same kernel. */

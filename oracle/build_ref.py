@@ -87,8 +87,8 @@ def build_shim(verbose=True):
     if not os.path.isdir(REF_SRC) or not os.path.exists(lib):
         return SHIM_BIN if os.path.exists(SHIM_BIN) else None
     harness = os.path.join(HERE, "shim_harness.cpp")
-    srcs = [harness, os.path.join(REPO, "include", "frc_b200.hpp"), os.path.join(REPO, "include", "remap_b200.h"),
-            __file__]
+    srcs = [harness, os.path.join(REPO, "include", "frc_b200.hpp"), os.path.join(REPO, "include", "fdf_b200.hpp"),
+            os.path.join(REPO, "include", "remap_b200.h"), lib, __file__]
     if os.path.exists(SHIM_BIN) and os.path.getmtime(SHIM_BIN) >= max(os.path.getmtime(p) for p in srcs):
         return SHIM_BIN
     os.makedirs(OUT_DIR, exist_ok=True)

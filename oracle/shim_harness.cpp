@@ -12,7 +12,13 @@
 //   number, position and the compressed image + compressed MEDIAN bytes; the callback sequence;
 //   and (fill_keys = 1) the kpr::grid contents handed to the callback.
 //
-// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1]     exit 0 = identical
+// With filter = 1 the reference's fragments then go through pass 2 twice,
+//   fdf::filter        (src/fdf.hpp:77-89)       -- the reference, CPU
+//   fdf_b200::filter   (include/fdf_b200.hpp)    -- rb_filter_fragment on the GPU
+// and the results are compared: per fragment zero, dimensions, every dot histogram, the frame list; per
+// callback the fragment index, frame number, position and the fde::mask image.
+//
+// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1] [filter 0|1]     exit 0 = identical
 
 #include <algorithm>
 #include <chrono>
@@ -30,6 +36,9 @@
 #include "frc.hpp"
 #include "nic.hpp"
 
+#include "fdf.hpp"
+
+#include "fdf_b200.hpp"
 #include "frc_b200.hpp"
 
 namespace {
@@ -66,6 +75,25 @@ struct native_compression {  // what main.cpp plugs in (src/main.cpp:112-125)
   template<typename Alloc>
   [[nodiscard]] icd::compressed_t operator()(sid::nat::aimg_t<Alloc> const& image) const {
     return nic::compress(image);
+  }
+  [[nodiscard]] sid::nat::dimg_t operator()(icd::compressed_t const& c, mrl::dimensions_t const& dim) const {
+    return nic::decompress(c, dim);
+  }
+};
+
+struct filter_rec {
+  std::size_t fragment, frame_no;
+  fgm::point_t pos;
+  std::vector<std::uint8_t> mask;
+};
+struct filter_recorder {
+  std::vector<filter_rec>* calls;
+  template<typename Contours, typename Mask>
+  void operator()(fgm::fragment const&, std::size_t frag, sid::nat::dimg_t const&, std::size_t no, sid::nat::dimg_t const&,
+                  fgm::point_t const& pos, Contours const&, Mask const& mask) {
+    filter_rec r{frag, no, pos, {}};
+    r.mask.assign(reinterpret_cast<std::uint8_t const*>(mask.data()), reinterpret_cast<std::uint8_t const*>(mask.end()));
+    calls->push_back(std::move(r));
   }
 };
 
@@ -127,6 +155,7 @@ int main(int argc, char** argv) {
   std::size_t const n = std::strtoul(argv[4], nullptr, 10), batch = std::strtoul(argv[5], nullptr, 10);
   bool const fill = std::atoi(argv[6]) != 0;
   bool const gpu_blit = argc > 7 && std::atoi(argv[7]) != 0;
+  bool const filter = argc > 8 && std::atoi(argv[8]) != 0;
   auto data = read_file(argv[1], w * h * n);
 
   std::vector<call_rec> ref_calls, gpu_calls;
@@ -184,6 +213,39 @@ int main(int argc, char** argv) {
     if (a.median != b.median) return fail("callback median", k);
     if (fill && !(a.keys == b.keys)) return fail("callback keys", k, a.keys.size());
     if (fill && a.weights != b.weights) return fail("callback weight counts", k);
+  }
+  if (filter) {
+    std::vector<fgm::fragment> frags;
+    for (auto& f : ref_frags) frags.push_back(std::move(f));
+    std::vector<filter_rec> rcalls, gcalls;
+    auto f0 = std::chrono::steady_clock::now();
+    auto rout = fdf::filter(frags, mrl::dimensions_t{w, h}, native_compression{}, filter_recorder{&rcalls});
+    auto f1 = std::chrono::steady_clock::now();
+    auto gout = fdf_b200::filter(frags, mrl::dimensions_t{w, h}, native_compression{}, filter_recorder{&gcalls});
+    auto f2 = std::chrono::steady_clock::now();
+    if (rout.size() != gout.size()) return fail("filter: fragment count", rout.size(), gout.size());
+    for (std::size_t k = 0; k < rout.size(); ++k) {
+      auto& a = rout[k];
+      auto& b = gout[k];
+      if (!(a.zero() == b.zero())) return fail("filter: zero", k);
+      if (a.dots().width() != b.dots().width() || a.dots().height() != b.dots().height()) return fail("filter: dimensions", k);
+      if (std::memcmp(a.dots().data(), b.dots().data(), a.dots().size() * sizeof(fgm::dot_type)) != 0) return fail("filter: dots", k);
+      if (a.frames().size() != b.frames().size()) return fail("filter: frame count", k);
+      for (std::size_t j = 0; j < a.frames().size(); ++j)
+        if (a.frames()[j].number_ != b.frames()[j].number_ || !(a.frames()[j].position_ == b.frames()[j].position_))
+          return fail("filter: frame record", k, j);
+    }
+    if (rcalls.size() != gcalls.size()) return fail("filter: callback count", rcalls.size(), gcalls.size());
+    for (std::size_t k = 0; k < rcalls.size(); ++k) {
+      auto& a = rcalls[k];
+      auto& b = gcalls[k];
+      if (a.fragment != b.fragment || a.frame_no != b.frame_no || !(a.pos == b.pos)) return fail("filter: callback order", k);
+      if (a.mask != b.mask) return fail("filter: fde::mask", k, a.frame_no);
+    }
+    std::printf("FILTER IDENTICAL: %zu fragments, %zu masks; fdf::filter %.1f ms, fdf_b200::filter %.1f ms\n", rout.size(),
+                rcalls.size(), std::chrono::duration<double, std::milli>(f1 - f0).count(),
+                std::chrono::duration<double, std::milli>(f2 - f1).count());
+    for (auto& f : frags) ref_frags.push_back(std::move(f));
   }
   std::printf("IDENTICAL: %zu fragments, %zu frames, %zu callbacks%s%s; reference %.1f ms, frc_b200 %.1f ms\n",
               ref_frags.size(), nframes, ref_calls.size(), fill ? " (keys compared)" : "", gpu_blit ? " (dots from rb_blit_blend)" : "",

@@ -23,7 +23,7 @@ SYMBOLS = [
     "rb_foreground_mask", "rb_foreground_mask_resident", "rb_synchronize", "rb_stream", "rb_kernel_times",
     "rb_kernel_launches", "rb_device_bytes", "rb_last_error", "rb_abi_version", "rb_offsets_device",
     "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count", "rb_register_host_async", "rb_blit_blend",
-    "rb_filter_fragment", "rb_filter_times",
+    "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
 ]
 
 
@@ -74,6 +74,8 @@ def load(build_if_missing: bool = False):
     lib.rb_blit_blend.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
     lib.rb_filter_fragment.restype = C.c_int
     lib.rb_filter_fragment.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.rb_upload_medians.restype = C.c_int
+    lib.rb_upload_medians.argtypes = [vp, vp, sz, sz]
     lib.rb_filter_times.restype = C.c_int
     lib.rb_filter_times.argtypes = [vp, C.POINTER(C.c_float), sz, C.POINTER(u32)]
     lib.rb_fetch_offsets.restype = C.c_int

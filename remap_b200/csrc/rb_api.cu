@@ -724,6 +724,24 @@ int rb_upload(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
   return RB_OK;
 }
 
+int rb_upload_medians(rb_ctx* c, const uint8_t* medians, size_t first, size_t n) {
+  if (!c || !medians) return RB_ERR_INVALID;
+  if (!c->d_median) { c->err = "rb_upload_medians: context created with compute_median = 0"; return RB_ERR_STATE; }
+  if (first + n > c->cfg.max_frames) { c->err = "rb_upload_medians: beyond max_frames"; return RB_ERR_CAPACITY; }
+  if (n == 0) return RB_OK;
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  // pixel x lives at byte x + 2 of a median row (the inverse of rb_fetch_medians)
+  RB_CUDA(c, cudaMemcpy2DAsync(c->d_median + g.median_stride * first + 2, g.mpitch, medians, g.W, g.W, (size_t)g.H * n,
+                               cudaMemcpyHostToDevice, c->stream));
+  if (c->med_hi == c->med_lo) { c->med_lo = first; c->med_hi = first + n; }
+  else {
+    if (first < c->med_lo) c->med_lo = first;
+    if (first + n > c->med_hi) c->med_hi = first + n;
+  }
+  return RB_OK;
+}
+
 // Picks the number of row segments per strip: enough CTAs for a few waves on every SM without
 // paying too many 4-row warm-ups.
 static uint32_t pick_segments(const rb_ctx* c, size_t n) {

@@ -156,33 +156,6 @@ RB_HD uint32_t interior_cols(uint32_t W, uint32_t w) {
   return m;
 }
 
-// id of the run that contains pixel (32 w + b, y); the pixel must be an interior pixel
-template <typename L>
-RB_HD uint32_t run_id(const RbFgWork<L>& s, uint32_t NW, uint32_t y, uint32_t w, uint32_t b) {
-  const uint32_t at = y * NW + w;
-  return s.rowbase[y] + s.base16[at] + rb_popc(s.start[at] & low_mask(b)) - 1u;
-}
-
-template <typename L>
-RB_HD uint32_t find_root(const L* parent, uint32_t a) {
-  for (;;) {
-    const uint32_t p = ld_label(parent + a);
-    if (p == a) return a;
-    a = p;
-  }
-}
-
-template <typename L>
-RB_HD void unite(L* parent, uint32_t a, uint32_t b) {
-  for (;;) {
-    a = find_root(parent, a);
-    b = find_root(parent, b);
-    if (a == b) return;
-    if (a < b) { const uint32_t t = a; a = b; b = t; }
-    if (cas_label(parent + a, a, b) == a) return;  // the larger root now points at the smaller one
-  }
-}
-
 // statistics slot of run k's component, RB_FG_NONE when the component holds no seed.  After the slot
 // phase a seeded root holds R + slot, every other run holds its root's id (< R).
 template <typename L>
@@ -250,103 +223,193 @@ RB_HD void build_word(const RbFgParams& p, const RbFgWork<L>& s, const RbPlaceme
   s.seed[at] = sd;
 }
 
-// Phase D: the unions of word (y, w).
-template <typename L>
-RB_HD void unite_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t y, uint32_t w) {
-  uint32_t e = s.ev[y * p.NW + w];
-  while (e) {
-    const uint32_t b = rb_ffs0(e);
-    e &= e - 1;
-    unite(s.parent, run_id(s, p.NW, y, w, b), run_id(s, p.NW, y - 1, w, b));
-  }
-}
-
-// Phase F: the seeds of word (y, w) mark their roots (parent[] is flat by now).
-template <typename L>
-RB_HD void seed_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t y, uint32_t w) {
-  const uint32_t at = y * p.NW + w;
-  const uint32_t sd = s.seed[at];
-  uint32_t e = sd & ~((sd << 1) & ~s.start[at]);  // a seed right of a seed of the same run adds nothing
-  while (e) {
-    const uint32_t b = rb_ffs0(e);
-    e &= e - 1;
-    const uint32_t r = s.parent[run_id(s, p.NW, y, w, b)];
-    a_or(s.seedbits + (r >> 5), 1u << (r & 31));
-  }
-}
-
-// Phase G: seeded roots that START in word (y, w) take a statistics slot.
-template <typename L>
-RB_HD void slot_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t y, uint32_t w) {
-  const uint32_t at = y * p.NW + w;
-  uint32_t e = s.start[at];
-  uint32_t k = s.rowbase[y] + s.base16[at];
-  while (e) {
-    e &= e - 1;
-    if ((s.seedbits[k >> 5] >> (k & 31)) & 1u) {  // only roots are ever marked
-      const uint32_t slot = rb_atomic_add(s.misc + 1, 1u);
-      if (slot < p.scap) {
-        s.parent[k] = (L)(R + slot);
-        s.area[slot] = 0;
-        s.yl[slot] = (y << 16) | 0xFFFFu;  // the root is the component's first run in row-major order: y = top row
-        s.maxx[slot] = 0;
-        s.maxy[slot] = 0;
-      }
-    }
-    ++k;
-  }
-}
-
-// Walks the run segments of word (y, w): fn(run id, first bit, last bit).
-template <typename L, typename Fn>
-RB_HD void for_segments(const RbFgParams& p, const RbFgWork<L>& s, uint32_t y, uint32_t w, Fn fn) {
-  const uint32_t at = y * p.NW + w;
-  const uint32_t cols = interior_cols(p.g.W, w);
-  if (!cols) return;
-  const uint32_t st = s.start[at];
-  const uint32_t top = 31u - (uint32_t)
+// ---- warp-lockstep item loops ---------------------------------------------------------------------
+// Every phase below is "for each word, for each set bit / run segment of the word".  The counts differ
+// from word to word, and a plain per-thread loop lets the lanes of a warp drift apart for good (measured:
+// 2 to 5 active lanes per issued instruction).  The loops are therefore written so that all lanes of a
+// warp take the same number of trips: RB_WARP_ANY(c) is a warp vote on the device (all 32 lanes must
+// reach it) and plain `c` in the host build.
 #if defined(__CUDA_ARCH__)
-      __clz((int)cols);
+#define RB_WARP_ANY(c) (__any_sync(0xFFFFFFFFu, (c)) != 0)
 #else
-      __builtin_clz(cols);
+#define RB_WARP_ANY(c) (c)
 #endif
-  uint32_t b = rb_ffs0(cols);
-  uint32_t k = s.rowbase[y] + s.base16[at] + rb_popc(st & low_mask(b)) - 1u;
+
+// find with path halving: any ancestor is a valid parent, so the plain store races harmlessly with other
+// finds; a CAS can only succeed on a root, and a root is never written here.
+template <typename L>
+RB_HD uint32_t find_halve(L* parent, uint32_t a) {
   for (;;) {
-    const uint32_t higher = b < 31 ? (st >> (b + 1)) << (b + 1) : 0u;
-    const uint32_t e = higher ? rb_ffs0(higher) - 1u : top;
-    fn(k, b, e);
-    if (e >= top) break;
-    b = e + 1;
-    ++k;
+    const uint32_t p = ld_label(parent + a);
+    if (p == a) return a;
+    const uint32_t gp = ld_label(parent + p);
+    if (gp == p) return p;
+    parent[a] = (L)gp;
+    a = gp;
   }
+}
+
+template <typename L>
+RB_HD void unite_halve(L* parent, uint32_t a, uint32_t b) {
+  for (;;) {
+    a = find_halve(parent, a);
+    b = find_halve(parent, b);
+    if (a == b) return;
+    if (a < b) { const uint32_t t = a; a = b; b = t; }
+    if (cas_label(parent + a, a, b) == a) return;  // the larger root now points at the smaller one
+  }
+}
+
+// Phase D: the unions of word `it` (on = this lane has a word).
+template <typename L>
+RB_HD void unite_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t it, bool on) {
+  const uint32_t y = on ? it / p.NW : 0;
+  on = on && y >= 2 && y + 3 <= p.g.H;
+  uint32_t e = on ? s.ev[it] : 0u;
+  uint32_t stc = 0, stu = 0, bc = 0, bu = 0;
+  if (e) {
+    stc = s.start[it]; stu = s.start[it - p.NW];
+    bc = s.rowbase[y] + s.base16[it] - 1u; bu = s.rowbase[y - 1] + s.base16[it - p.NW] - 1u;
+  }
+  while (RB_WARP_ANY(e != 0)) {
+    if (e) {
+      const uint32_t lm = low_mask(rb_ffs0(e));
+      e &= e - 1;
+      unite_halve(s.parent, bc + rb_popc(stc & lm), bu + rb_popc(stu & lm));
+    }
+  }
+}
+
+// Phase E: label k -> its root.
+template <typename L>
+RB_HD void flatten_label(const RbFgWork<L>& s, uint32_t k, bool on) {
+  uint32_t r = on ? k : 0;
+  bool go = on;
+  while (RB_WARP_ANY(go)) {
+    if (go) {
+      const uint32_t q = ld_label(s.parent + r);
+      if (q == r) go = false; else r = q;
+    }
+  }
+  if (on) s.parent[k] = (L)r;
+}
+
+// Phase F: the seeds of word `it` mark their roots (parent[] is flat by now).
+template <typename L>
+RB_HD void seed_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t it, bool on) {
+  uint32_t e = 0, st = 0, base = 0;
+  if (on) {
+    const uint32_t sd = s.seed[it];
+    st = s.start[it];
+    e = sd & ~((sd << 1) & ~st);  // a seed right of a seed of the same run adds nothing
+    if (e) base = s.rowbase[it / p.NW] + s.base16[it] - 1u;
+  }
+  while (RB_WARP_ANY(e != 0)) {
+    if (e) {
+      const uint32_t lm = low_mask(rb_ffs0(e));
+      e &= e - 1;
+      const uint32_t r = s.parent[base + rb_popc(st & lm)];
+      a_or(s.seedbits + (r >> 5), 1u << (r & 31));
+    }
+  }
+}
+
+// Phase G: seeded roots that START in word `it` take a statistics slot.
+template <typename L>
+RB_HD void slot_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t it, bool on) {
+  if (!on) return;
+  const uint32_t n = rb_popc(s.start[it]);
+  if (!n) return;
+  const uint32_t y = it / p.NW, k0 = s.rowbase[y] + s.base16[it];
+  // the seed marks of runs k0 .. k0 + n - 1 (n <= 32) as one word
+  const uint32_t lo = s.seedbits[k0 >> 5] >> (k0 & 31);
+  const uint32_t hi = (k0 & 31) && ((k0 + n - 1) >> 5) != (k0 >> 5) ? s.seedbits[(k0 >> 5) + 1] << (32 - (k0 & 31)) : 0u;
+  uint32_t m = (lo | hi) & low_mask(n - 1);
+  while (m) {  // only roots are ever marked; few per word
+    const uint32_t k = k0 + rb_ffs0(m);
+    m &= m - 1;
+    const uint32_t slot = rb_atomic_add(s.misc + 1, 1u);
+    if (slot < p.scap) {
+      s.parent[k] = (L)(R + slot);
+      s.area[slot] = 0;
+      s.yl[slot] = (y << 16) | 0xFFFFu;  // the root is the component's first run in row-major order: y = top row
+      s.maxx[slot] = 0;
+      s.maxy[slot] = 0;
+    }
+  }
+}
+
+// Iterator over the run segments of one word: (run id k, first bit b, last bit e).
+struct RbFgSeg {
+  uint32_t st, top, b, k;
+  bool more;
+};
+template <typename L>
+RB_HD RbFgSeg seg_begin(const RbFgParams& p, const RbFgWork<L>& s, uint32_t it, bool on) {
+  RbFgSeg g;
+  g.st = g.top = g.b = g.k = 0;
+  g.more = false;
+  if (!on) return g;
+  const uint32_t y = it / p.NW, w = it - y * p.NW;
+  const uint32_t cols = interior_cols(p.g.W, w);
+  if (!cols || y < 1 || y + 3 > p.g.H) return g;
+  g.st = s.start[it];
+#if defined(__CUDA_ARCH__)
+  g.top = 31u - (uint32_t)__clz((int)cols);
+#else
+  g.top = 31u - (uint32_t)__builtin_clz(cols);
+#endif
+  g.b = rb_ffs0(cols);
+  g.k = s.rowbase[y] + s.base16[it] + rb_popc(g.st & low_mask(g.b)) - 1u;
+  g.more = true;
+  return g;
+}
+RB_HD uint32_t seg_end(const RbFgSeg& g) {  // last bit of the current segment
+  const uint32_t higher = g.b < 31 ? (g.st >> (g.b + 1)) << (g.b + 1) : 0u;
+  return higher ? rb_ffs0(higher) - 1u : g.top;
+}
+RB_HD void seg_next(RbFgSeg& g, uint32_t e) {
+  if (e >= g.top) { g.more = false; return; }
+  g.b = e + 1;
+  ++g.k;
 }
 
 // Phase H: statistics of the seeded components.
 template <typename L>
-RB_HD void stats_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t y, uint32_t w) {
-  for_segments(p, s, y, w, [&](uint32_t k, uint32_t b, uint32_t e) {
-    const uint32_t slot = slot_of(s, R, k);
-    if (slot == RB_FG_NONE) return;
-    const uint32_t x0 = 32u * w + b, x1 = 32u * w + e;
-    rb_atomic_add(s.area + slot, e - b + 1u);
-    if (x1 > s.maxx[slot]) a_max(s.maxx + slot, x1);
-    if (y > s.maxy[slot]) a_max(s.maxy + slot, y);
-    const uint32_t yl = s.yl[slot];
-    if (y > (yl >> 16) && x0 < (yl & 0xFFFFu)) a_min(s.yl + slot, (yl & 0xFFFF0000u) | x0);
-  });
+RB_HD void stats_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t it, bool on) {
+  RbFgSeg g = seg_begin(p, s, it, on);
+  const uint32_t y = it / p.NW, x32 = 32u * (it - y * p.NW);
+  while (RB_WARP_ANY(g.more)) {
+    if (g.more) {
+      const uint32_t e = seg_end(g);
+      const uint32_t slot = slot_of(s, R, g.k);
+      if (slot != RB_FG_NONE) {
+        const uint32_t x0 = x32 + g.b, x1 = x32 + e;
+        rb_atomic_add(s.area + slot, e - g.b + 1u);
+        if (x1 > s.maxx[slot]) a_max(s.maxx + slot, x1);
+        if (y > s.maxy[slot]) a_max(s.maxy + slot, y);
+        const uint32_t yl = s.yl[slot];
+        if (y > (yl >> 16) && x0 < (yl & 0xFFFFu)) a_min(s.yl + slot, (yl & 0xFFFF0000u) | x0);
+      }
+      seg_next(g, e);
+    }
+  }
 }
 
 // Phase I: kept components paint their runs (every word is written by exactly one item).
 template <typename L>
-RB_HD void paint_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t y, uint32_t w) {
+RB_HD void paint_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint32_t it, bool on) {
+  RbFgSeg g = seg_begin(p, s, it, on);
   uint32_t out = 0;
-  if (y >= 1 && y + 3 <= p.g.H)
-    for_segments(p, s, y, w, [&](uint32_t k, uint32_t b, uint32_t e) {
-      const uint32_t slot = slot_of(s, R, k);
-      if (slot != RB_FG_NONE && s.area[slot] <= p.area_limit) out |= low_mask(e) & ~(low_mask(b) >> 1);
-    });
-  s.ev[y * p.NW + w] = out;
+  while (RB_WARP_ANY(g.more)) {
+    if (g.more) {
+      const uint32_t e = seg_end(g);
+      const uint32_t slot = slot_of(s, R, g.k);
+      if (slot != RB_FG_NONE && s.area[slot] <= p.area_limit) out |= low_mask(e) & ~(low_mask(g.b) >> 1);
+      seg_next(g, e);
+    }
+  }
+  if (on) s.ev[it] = out;
 }
 
 // Phase J: lane `lane` of the warp that paints slot `slot`'s enclosure (src/fde.hpp:133-143).
@@ -424,36 +487,31 @@ RB_HD bool frame_body(const RbFgParams& p, const RbFgWork<L>& s, uint32_t i, uin
     for (uint32_t k = tid; k < (R + 31) / 32; k += NT) s.seedbits[k] = 0;
   }
   RB_SYNC();
+  // the item loops below run the same number of trips in every lane (see RB_WARP_ANY)
   RB_FOR_THREADS(tid, NT) {  // D: unions
-    for (uint32_t it = tid; it < nwords; it += NT) {
-      const uint32_t y = it / NW;
-      if (y >= 2 && y + 3 <= H) unite_word(p, s, y, it % NW);
-    }
+    for (uint32_t base = 0; base < nwords; base += NT) unite_word(p, s, base + tid, base + tid < nwords);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // E: flatten
-    for (uint32_t k = tid; k < R; k += NT) s.parent[k] = (L)find_root(s.parent, k);
+    for (uint32_t base = 0; base < R; base += NT) flatten_label(s, base + tid, base + tid < R);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // F: seeds
-    for (uint32_t it = tid; it < nwords; it += NT) seed_word(p, s, it / NW, it % NW);
+    for (uint32_t base = 0; base < nwords; base += NT) seed_word(p, s, base + tid, base + tid < nwords);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // G: slots
-    for (uint32_t it = tid; it < nwords; it += NT) slot_word(p, s, R, it / NW, it % NW);
+    for (uint32_t base = 0; base < nwords; base += NT) slot_word(p, s, R, base + tid, base + tid < nwords);
   }
   RB_SYNC();
   const uint32_t nslots = s.misc[1];
   if (nslots > p.scap) return false;
   RB_FOR_THREADS(tid, NT) {  // H: statistics
-    for (uint32_t it = tid; it < nwords; it += NT) {
-      const uint32_t y = it / NW;
-      if (y >= 1 && y + 3 <= H) stats_word(p, s, R, y, it % NW);
-    }
+    for (uint32_t base = 0; base < nwords; base += NT) stats_word(p, s, R, base + tid, base + tid < nwords);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // I: runs of the kept components
-    for (uint32_t it = tid; it < nwords; it += NT) paint_word(p, s, R, it / NW, it % NW);
+    for (uint32_t base = 0; base < nwords; base += NT) paint_word(p, s, R, base + tid, base + tid < nwords);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // J: enclosures

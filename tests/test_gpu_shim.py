@@ -18,17 +18,17 @@ SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
 pytestmark = pytest.mark.gpu
 
 
-def _run(frames, batch, fill, tmp_path, gpu_blit=False):
+def _run(frames, batch, fill, tmp_path, gpu_blit=False, filter=False):
     if not os.path.exists(SHIM):
         pytest.fail("oracle/_ref/shim_harness missing: run `python oracle/build_ref.py` in the build container")
     n, H, W = frames.shape
     path = os.path.join(tmp_path, "frames.bin")
     np.ascontiguousarray(frames, np.uint8).tofile(path)
-    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill)), str(int(gpu_blit))], capture_output=True,
+    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill)), str(int(gpu_blit)), str(int(filter))], capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
-    assert r.stdout.startswith("IDENTICAL"), r.stdout
-    return r.stdout
+    assert "\nIDENTICAL" in "\n" + r.stdout, r.stdout
+    return r.stdout[r.stdout.index("IDENTICAL"):] if not filter else r.stdout
 
 
 @pytest.mark.parametrize("batch", [2, 7, 64])
@@ -57,3 +57,11 @@ def test_collector_shim_with_gpu_map_assembly(batch, tmp_path):
     seq = synth.scrolling_tilemap(120, 320, 224, seed=13, cut_every=45, vmax=(9, 7))
     out = _run(seq.frames, batch, False, str(tmp_path), gpu_blit=True)
     assert "dots from rb_blit_blend" in out and int(out.split()[1]) >= 2, out
+
+
+def test_filter_shim_matches_reference_fdf_filter(tmp_path):
+    """include/fdf_b200.hpp (rb_filter_fragment) against the reference's fdf::filter on the reference
+    collector's own fragments: filtered dots, frame lists and every fde::mask handed to the callback."""
+    seq = synth.scrolling_tilemap(90, 320, 224, seed=21, sprites=6, cut_every=40)
+    out = _run(seq.frames, 32, False, str(tmp_path), filter=True)
+    assert "FILTER IDENTICAL" in out and "90 masks" in out, out
