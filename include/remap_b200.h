@@ -187,6 +187,33 @@ int rb_upload_medians(rb_ctx* ctx, const uint8_t* medians, size_t first, size_t 
  * global-memory variant of the same kernel. */
 int rb_filter_times(rb_ctx* ctx, float* ms, size_t n, uint32_t* frames_deferred);
 
+/* Fragment splicing: the device side of fgs::splice (src/fgs.hpp:187-213).  A snippet is what
+ * fgs::details::extract_single (src/fgs.hpp:80-89) makes of a fragment: blend() image + mask and the keypoints of
+ * kpe::extractor<kpr::grid<1, 1>, 0> over the whole map image; it lives on the device.  dots = H*W*16 uint16
+ * (fgm::fragment::dots()).  Snippets have no rb_ctx; each owns a stream on `device`. */
+typedef struct rb_snippet rb_snippet;
+int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, rb_snippet** out);
+void rb_snippet_destroy(rb_snippet* s);
+const char* rb_snippet_last_error(rb_snippet* s);
+/* Parity tap: keypoint count, blend image / mask (H*W bytes each), keypoint records (unordered). Any may be NULL. */
+int rb_snippet_fetch(rb_snippet* s, uint32_t* nkeypoints, uint8_t* out_image, uint8_t* out_mask, rb_keypoint* out_kps, size_t cap);
+
+/* kpm::match, cellular variant (src/kpm.hpp:371-393), of two snippets: every pair of equal codes votes
+ * prev - curr (count_offsets, :231-262), the offset with the most votes wins (find_best, :280-299), and it is
+ * accepted iff its votes fall into at least 0.66 x the active cells (count_active_cells, :349-369, :387-389).
+ * find_best takes the FIRST maximum in std::unordered_map iteration order, which is implementation-defined;
+ * here ties go to the smallest (dy, dx) and `ties` > 1 reports that the reference's choice is not defined. */
+typedef struct rb_cell_match {
+  uint32_t valid;              /* the std::optional<kpm::vote> has a value                    */
+  int32_t dx, dy;              /* vote.offset_ (prev - curr)                                   */
+  uint32_t matched_keypoints;  /* vote.count_                                                  */
+  uint32_t matched_cells, active_cells;
+  uint32_t offsets;            /* distinct offsets that received a vote                        */
+  uint32_t ties;               /* offsets sharing the largest vote count                       */
+  uint64_t pairs;              /* all votes                                                    */
+} rb_cell_match;
+int rb_snippet_match(rb_snippet* prev, rb_snippet* curr, uint32_t cell_w, uint32_t cell_h, rb_cell_match* out);
+
 /* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
  * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */
 const rb_offset* rb_offsets_device(rb_ctx* ctx);

@@ -52,7 +52,7 @@ PATCHES = [
 DEAD_MEMBER_RE = re.compile(
     r"\n  inline \[\[nodiscard\]\] __m256i get_unit(?:_low|_hi)?\(.*?\n  \}\n", re.S)
 
-FILES = ["all.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fdf.hpp", "fgm.hpp",
+FILES = ["all.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fdf.hpp", "fgm.hpp", "fgs.hpp",
          "frc.hpp", "icd.hpp", "ifd.hpp", "kpe.hpp", "kpm.hpp", "kpr.hpp", "mrl.hpp",
          "nic.hpp", "sid.hpp"]
 
@@ -88,6 +88,7 @@ def build_shim(verbose=True):
         return SHIM_BIN if os.path.exists(SHIM_BIN) else None
     harness = os.path.join(HERE, "shim_harness.cpp")
     srcs = [harness, os.path.join(REPO, "include", "frc_b200.hpp"), os.path.join(REPO, "include", "fdf_b200.hpp"),
+            os.path.join(REPO, "include", "fgs_b200.hpp"),
             os.path.join(REPO, "include", "remap_b200.h"), lib, __file__]
     if os.path.exists(SHIM_BIN) and os.path.getmtime(SHIM_BIN) >= max(os.path.getmtime(p) for p in srcs):
         return SHIM_BIN

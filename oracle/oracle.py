@@ -26,6 +26,9 @@ RESULT_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("valid", "<u4"), ("tie_s
                          ("top_score", "<u4", (2,)), ("ntop", "<u4")])
 CONTOUR_DTYPE = np.dtype([("area", "<u4"), ("left", "<u4"), ("top", "<u4"), ("right", "<u4"), ("bottom", "<u4"),
                           ("colour", "<u4")])
+CELL_MATCH_DTYPE = np.dtype([("valid", "<u4"), ("dx", "<i4"), ("dy", "<i4"), ("matched_keypoints", "<u4"),
+                             ("matched_cells", "<u4"), ("active_cells", "<u4"), ("offsets", "<u4"), ("ties", "<u4"),
+                             ("pairs", "<u8")])
 
 
 class Config(C.Structure):
@@ -70,12 +73,16 @@ def lib():
         _lib.ro_foreground.restype = C.c_size_t
         _lib.ro_foreground.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib.ro_cell_match.restype = None
+        _lib.ro_cell_match.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.ro_luts.restype = None
         _lib.ro_luts.argtypes = [C.c_void_p, C.c_void_p]
         _lib.ro_sections.restype = None
         _lib.ro_sections.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p]
         for fn, dt in (("ro_sizeof_keypoint", KP_DTYPE), ("ro_sizeof_region_vote", VOTE_DTYPE),
-                       ("ro_sizeof_match_result", RESULT_DTYPE), ("ro_sizeof_contour", CONTOUR_DTYPE)):
+                       ("ro_sizeof_match_result", RESULT_DTYPE), ("ro_sizeof_contour", CONTOUR_DTYPE),
+                       ("ro_sizeof_cell_match", CELL_MATCH_DTYPE)):
             f = getattr(_lib, fn)
             f.restype = C.c_size_t
             assert f() == dt.itemsize, (fn, f(), dt.itemsize)
@@ -236,3 +243,28 @@ def filter_fragment(frames, medians, pos, mapW, mapH, background=None):
         nc[f] = len(cont)
         dots[y:y + H, x:x + W] += ((frames[f][:, :, None] == ar) & (m[:, :, None] == 0)).astype(np.uint16)
     return dict(background=background, masks=masks, ncontours=nc, dots=dots)
+
+
+def blend(dots):
+    """fgm::fragment::blend (src/fgm.hpp:115-135): -> (image, mask)"""
+    best = dots.max(axis=2)
+    return np.where(best != 0, dots.argmax(axis=2), 0).astype(np.uint8), (best != 0).astype(np.uint8)
+
+
+def snippet(dots):
+    """fgs::details::extract_single (src/fgs.hpp:80-89): blend + kpe with a 1 x 1 grid, no overlap.
+    -> dict(image, mask, kps)"""
+    image, mask = blend(dots)
+    H, W = image.shape
+    _, kps = extract(config(W, H, 1, 1, 0), image)
+    return dict(image=image, mask=mask, kps=kps)
+
+
+def cell_match(prev, curr, cell=(15, 15)):
+    """The cellular kpm::match (src/kpm.hpp:371-393) of two snippets (dicts from snippet())."""
+    pk, ck = np.ascontiguousarray(prev["kps"]), np.ascontiguousarray(curr["kps"])
+    pm = np.ascontiguousarray(prev["mask"], np.uint8)
+    res = np.zeros(1, CELL_MATCH_DTYPE)
+    lib().ro_cell_match(_p(pk), len(pk), _p(pm), pm.shape[1], pm.shape[0], _p(ck), len(ck), curr["mask"].shape[1],
+                        curr["mask"].shape[0], cell[0], cell[1], _p(res))
+    return res[0]

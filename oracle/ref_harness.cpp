@@ -18,6 +18,10 @@
 //                                           (src/fdf.hpp:40-91) over the collected fragments: dumps every
 //                                           frame's foreground contours and fde::mask, the backgrounds and
 //                                           the filtered fragments' dots; R > 1 repeats fdf::filter for timing
+//   splice <frames.bin> W H N <out.bin>     frc::collector::collect + complete, then (a) every fragment as a
+//                                           fgs snippet (blend, kpe with a 1x1 grid, src/fgs.hpp:80-89) and the
+//                                           cellular kpm::match (src/kpm.hpp:371-393) of every snippet pair with
+//                                           its intermediates, (b) fgs::splice (src/fgs.hpp:187-213) itself
 //
 // frames.bin = N*H*W bytes, row-major, values 0..15 (== nil::read_raw format, src/nil.hpp:24).
 
@@ -37,6 +41,7 @@
 
 #include "fde.hpp"
 #include "fdf.hpp"
+#include "fgs.hpp"
 #include "frc.hpp"
 #include "nic.hpp"
 
@@ -412,6 +417,106 @@ int run_filter(int argc, char** argv) {
   return 0;
 }
 
+// ---- fragment splicing: fgs::splice ---------------------------------------------------------
+void dump_fragment(FILE* out, fgm::fragment const& f) {
+  put32(out, static_cast<std::uint32_t>(f.dots().width()));
+  put32(out, static_cast<std::uint32_t>(f.dots().height()));
+  puti32(out, f.zero().x_); puti32(out, f.zero().y_);
+  put32(out, static_cast<std::uint32_t>(f.frames().size()));
+  for (auto& fr : f.frames()) {
+    put32(out, static_cast<std::uint32_t>(fr.number_));
+    puti32(out, fr.position_.x_); puti32(out, fr.position_.y_);
+  }
+  std::fwrite(f.dots().data(), sizeof(fgm::dot_type), f.dots().size(), out);
+}
+
+int run_splice(int argc, char** argv) {
+  if (argc < 7) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  auto frames = read_file(argv[2], N * W * H);
+  mrl::dimensions_t const dim{W, H};
+  std::vector<fgm::fragment> fragments;
+  {
+    frc::collector collector{dim};
+    memory_feed feed{frames.data(), W, H, 0, N};
+    collector.collect(feed, native_codec{},
+                      [](fgm::fragment const&, frc::frame_type const&, frc::image_type const&, frc::grid_type const&) {});
+    auto list = collector.complete();
+    for (auto& f : list) fragments.push_back(std::move(f));
+  }
+  FILE* out = std::fopen(argv[6], "wb");
+  if (!out) return 2;
+  std::fwrite("RMSP", 1, 4, out);
+  put32(out, W); put32(out, H); put32(out, N);
+  put32(out, static_cast<std::uint32_t>(fragments.size()));
+  for (auto& f : fragments) dump_fragment(out, f);
+
+  // (a) the snippets and every pairwise cellular match, in the order fgs::details::match_all makes them
+  std::vector<fgs::details::snippet> snips;
+  for (auto& f : fragments) snips.push_back(fgs::details::extract_single(fgm::fragment{f}));
+  for (auto& sn : snips) {
+    auto& reg = sn.grid_[0];
+    std::vector<kp_rec> recs;
+    for (auto& [code, pts] : reg.points())
+      for (auto& p : pts) {
+        kp_rec r;
+        r.x = static_cast<std::uint16_t>(p.x_); r.y = static_cast<std::uint16_t>(p.y_);
+        std::memcpy(r.code, code.data(), 13);
+        recs.push_back(r);
+      }
+    std::sort(recs.begin(), recs.end(), [](kp_rec const& a, kp_rec const& b) { return a.y != b.y ? a.y < b.y : a.x < b.x; });
+    put32(out, static_cast<std::uint32_t>(sn.mask_.width()));
+    put32(out, static_cast<std::uint32_t>(sn.mask_.height()));
+    put32(out, static_cast<std::uint32_t>(recs.size()));
+    for (auto& r : recs) { std::fwrite(&r.x, 2, 1, out); std::fwrite(&r.y, 2, 1, out); std::fwrite(r.code, 1, 13, out); }
+    std::fwrite(sn.mask_.data(), 1, sn.mask_.size(), out);
+  }
+  constexpr kpm::cell_size_t cell{15, 15};  // src/fgs.hpp:121
+  for (std::size_t i = 0; i < snips.size(); ++i)
+    for (std::size_t j = i + 1; j < snips.size(); ++j) {
+      auto& a = snips[i];
+      auto& b = snips[j];
+      auto totals = kpm::details::count_offsets(a.grid_[0], b.grid_[0], cell);
+      put32(out, static_cast<std::uint32_t>(i)); put32(out, static_cast<std::uint32_t>(j));
+      put32(out, static_cast<std::uint32_t>(totals.size()));
+      std::uint64_t pairs = 0;
+      std::size_t best_kp = 0, ties = 0;
+      for (auto& [off, cells] : totals) {
+        std::size_t kp = 0;
+        for (auto& [c, n] : cells) kp += n;
+        pairs += kp;
+        if (kp > best_kp) { best_kp = kp; ties = 1; }
+        else if (kp == best_kp) ++ties;
+      }
+      std::fwrite(&pairs, 8, 1, out);
+      put32(out, static_cast<std::uint32_t>(ties));  // offsets sharing the largest matched_keypoints
+      if (!totals.empty()) {
+        auto best = kpm::details::find_best(totals);
+        auto active = kpm::details::count_active_cells(a.grid_[0], a.mask_, b.grid_[0], b.mask_, best.offset_, cell);
+        puti32(out, best.offset_.x_); puti32(out, best.offset_.y_);
+        put32(out, static_cast<std::uint32_t>(best.matched_keypoints_));
+        put32(out, static_cast<std::uint32_t>(best.matched_cells_));
+        put32(out, static_cast<std::uint32_t>(active));
+      }
+      auto vote = kpm::match(a.grid_[0], a.mask_, b.grid_[0], b.mask_, cell);  // the reference's own verdict
+      put32(out, vote ? 1u : 0u);
+      puti32(out, vote ? vote->offset_.x_ : 0); puti32(out, vote ? vote->offset_.y_ : 0);
+      put32(out, vote ? static_cast<std::uint32_t>(vote->count_) : 0u);
+    }
+
+  // (b) fgs::splice on copies of the fragments
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<fgm::fragment> copy{fragments};
+  auto spliced = fgs::splice(copy.begin(), copy.end());
+  auto t1 = std::chrono::steady_clock::now();
+  put32(out, static_cast<std::uint32_t>(spliced.size()));
+  for (auto& f : spliced) dump_fragment(out, f);
+  std::fclose(out);
+  std::printf("{\"mode\": \"splice\", \"frames\": %zu, \"fragments\": %zu, \"spliced\": %zu, \"splice_s\": %.6f}\n", N,
+              fragments.size(), spliced.size(), std::chrono::duration<double>(t1 - t0).count());
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -421,5 +526,6 @@ int main(int argc, char** argv) {
   if (mode == "bench") return run_bench(argc, argv);
   if (mode == "mask") return run_mask(argc, argv);
   if (mode == "filter") return run_filter(argc, argv);
+  if (mode == "splice") return run_splice(argc, argv);
   return 1;
 }

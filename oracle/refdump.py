@@ -162,3 +162,75 @@ def ref_filter(frames: np.ndarray, reps: int = 1) -> dict:
             d = parse_filter_dump(f.read())
     d["timing"] = json.loads(out.decode().strip().splitlines()[-1])
     return d
+
+
+def _read_fragment(buf, pos):
+    w, h, zx, zy, nf = struct.unpack_from("<IIiiI", buf, pos)
+    pos += 20
+    fr = np.frombuffer(buf, "<i4", nf * 3, pos).reshape(nf, 3).copy()   # number, x, y
+    pos += nf * 12
+    dots = np.frombuffer(buf, "<u2", w * h * 16, pos).reshape(h, w, 16).copy()
+    pos += w * h * 32
+    return dict(zero=(zx, zy), frames=fr, dots=dots), pos
+
+
+SNIP_KP_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("code", "u1", (13,))])
+
+
+def parse_splice_dump(buf: bytes) -> dict:
+    """Dump of `ref_harness splice`: fragments, fgs snippets, every pairwise cellular kpm::match, fgs::splice."""
+    assert buf[:4] == b"RMSP"
+    W, H, N, nfrag = struct.unpack_from("<IIII", buf, 4)
+    pos = 20
+    fragments = []
+    for _ in range(nfrag):
+        f, pos = _read_fragment(buf, pos)
+        fragments.append(f)
+    snippets = []
+    for _ in range(nfrag):
+        w, h, nk = struct.unpack_from("<III", buf, pos)
+        pos += 12
+        kps = np.frombuffer(buf, SNIP_KP_DTYPE, nk, pos).copy()
+        pos += nk * SNIP_KP_DTYPE.itemsize
+        mask = np.frombuffer(buf, np.uint8, w * h, pos).reshape(h, w).copy()
+        pos += w * h
+        snippets.append(dict(kps=kps, mask=mask))
+    matches = []
+    for i in range(nfrag):
+        for j in range(i + 1, nfrag):
+            a, b, noff = struct.unpack_from("<III", buf, pos)
+            pos += 12
+            (pairs,) = struct.unpack_from("<Q", buf, pos)
+            pos += 8
+            (ties,) = struct.unpack_from("<I", buf, pos)
+            pos += 4
+            m = dict(prev=a, curr=b, offsets=noff, pairs=pairs, ties=ties)
+            if noff:
+                dx, dy, kp, cells, active = struct.unpack_from("<iiIII", buf, pos)
+                pos += 20
+                m.update(best=(dx, dy), matched_keypoints=kp, matched_cells=cells, active_cells=active)
+            valid, vx, vy, cnt = struct.unpack_from("<IiiI", buf, pos)
+            pos += 16
+            m.update(valid=bool(valid), vote=(vx, vy), count=cnt)
+            matches.append(m)
+    (ns,) = struct.unpack_from("<I", buf, pos)
+    pos += 4
+    spliced = []
+    for _ in range(ns):
+        f, pos = _read_fragment(buf, pos)
+        spliced.append(f)
+    assert pos == len(buf), (pos, len(buf))
+    return dict(W=W, H=H, N=N, fragments=fragments, snippets=snippets, matches=matches, spliced=spliced)
+
+
+def ref_splice(frames: np.ndarray) -> dict:
+    assert have_ref()
+    N, H, W = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "frames.bin"), os.path.join(td, "dump.bin")
+        np.ascontiguousarray(frames, np.uint8).tofile(fin)
+        out = subprocess.check_output([REF_BIN, "splice", fin, str(W), str(H), str(N), fout])
+        with open(fout, "rb") as f:
+            d = parse_splice_dump(f.read())
+    d["timing"] = json.loads(out.decode().strip().splitlines()[-1])
+    return d

@@ -549,6 +549,113 @@ size_t ro_foreground(const uint8_t* bg, uint32_t bgW, uint32_t bgH, int32_t px, 
 }
 size_t ro_sizeof_contour(void) { return sizeof(ro_contour); }
 
+/* ---- f3: the cellular kpm::match used by fragment splicing (src/kpm.hpp:225-393, called from
+ * fgs::details::match_partial, src/fgs.hpp:119-134, with cell_size {15, 15}) --------------------------
+ *
+ *   count_offsets (:249-262) / get_offsets (:231-247): for every code present in both regions, ALL pairs
+ *     (prev point, curr point) vote for offset prev - curr; the vote is filed under the cell
+ *     (min(px, cx) / cw, min(py, cy) / ch) (to_cell, :225-229);
+ *   find_best (:280-299): per offset matched_cells = distinct cells, matched_keypoints = votes; the offset with
+ *     the most votes wins -- std::max_element over an unordered_map, i.e. the FIRST maximum in an
+ *     implementation-defined order.  Here ties go to the smallest (dy, dx) and `ties` reports how many offsets
+ *     share the maximum (> 1: the reference's choice is not defined by the language);
+ *   count_active_cells (:349-369) -> filter_keypoints (:321-347): curr points inside clim (get_limits, :301-315,
+ *     in size_t arithmetic) whose position + offset hits a set pixel of prev's mask; distinct cells relative
+ *     to clim's corner;
+ *   match (:371-393): no common code -> nullopt; matched_cells < active * 0.66f -> nullopt; else the vote. */
+typedef struct {
+  uint32_t valid;
+  int32_t dx, dy;
+  uint32_t matched_keypoints, matched_cells, active_cells, offsets, ties;
+  uint64_t pairs;
+} ro_cell_match_result;
+
+typedef struct { int32_t oy, ox; uint32_t cy, cx; } ro_cell_vote;
+
+static int ro_cell_vote_cmp(const void* a, const void* b) {
+  const ro_cell_vote* x = (const ro_cell_vote*)a;
+  const ro_cell_vote* y = (const ro_cell_vote*)b;
+  if (x->oy != y->oy) return x->oy < y->oy ? -1 : 1;
+  if (x->ox != y->ox) return x->ox < y->ox ? -1 : 1;
+  if (x->cy != y->cy) return x->cy < y->cy ? -1 : 1;
+  if (x->cx != y->cx) return x->cx < y->cx ? -1 : 1;
+  return 0;
+}
+static int ro_kp_code_cmp(const void* a, const void* b) {
+  return memcmp(((const ro_keypoint*)a)->code, ((const ro_keypoint*)b)->code, RO_CODE_LEN);
+}
+static void ro_cell_limits(int32_t delta, uint64_t previous, uint64_t current, uint64_t* lo, uint64_t* hi) {
+  if (delta < 0) { /* src/kpm.hpp:304-309: the `second` (curr) span */
+    const uint64_t d = (uint64_t)(-(int64_t)delta);
+    *lo = d;
+    *hi = current < previous + d ? current : previous + d;
+  } else {         /* src/kpm.hpp:312-313 */
+    *lo = 0;
+    *hi = current < previous - (uint64_t)delta ? current : previous - (uint64_t)delta;
+  }
+}
+
+void ro_cell_match(const ro_keypoint* prev, size_t np, const uint8_t* pmask, uint32_t pW, uint32_t pH,
+                   const ro_keypoint* curr, size_t nc, uint32_t cW, uint32_t cH, uint32_t cell_w, uint32_t cell_h,
+                   ro_cell_match_result* res) {
+  memset(res, 0, sizeof(*res));
+  ro_keypoint* ps = (ro_keypoint*)malloc((np + 1) * sizeof(ro_keypoint));
+  memcpy(ps, prev, np * sizeof(ro_keypoint));
+  qsort(ps, np, sizeof(ro_keypoint), ro_kp_code_cmp);
+  size_t cap = 1024, nv = 0;
+  ro_cell_vote* votes = (ro_cell_vote*)malloc(cap * sizeof(ro_cell_vote));
+  for (size_t j = 0; j < nc; ++j) {
+    size_t lo = 0, hi = np; /* first prev entry with code >= curr's */
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (memcmp(ps[mid].code, curr[j].code, RO_CODE_LEN) < 0) lo = mid + 1; else hi = mid;
+    }
+    for (size_t i = lo; i < np && memcmp(ps[i].code, curr[j].code, RO_CODE_LEN) == 0; ++i) {
+      if (nv == cap) { cap *= 2; votes = (ro_cell_vote*)realloc(votes, cap * sizeof(ro_cell_vote)); }
+      const int32_t px = ps[i].x, py = ps[i].y, cx = curr[j].x, cy = curr[j].y;
+      votes[nv].ox = px - cx; votes[nv].oy = py - cy;
+      votes[nv].cx = (uint32_t)((px < cx ? px : cx) / (int32_t)cell_w);
+      votes[nv].cy = (uint32_t)((py < cy ? py : cy) / (int32_t)cell_h);
+      ++nv;
+    }
+  }
+  res->pairs = nv;
+  if (nv == 0) { free(ps); free(votes); return; }
+  qsort(votes, nv, sizeof(ro_cell_vote), ro_cell_vote_cmp);
+  uint32_t best_kp = 0, best_cells = 0;
+  for (size_t a = 0; a < nv;) {
+    size_t b = a;
+    uint32_t cells = 0;
+    while (b < nv && votes[b].oy == votes[a].oy && votes[b].ox == votes[a].ox) {
+      if (b == a || votes[b].cy != votes[b - 1].cy || votes[b].cx != votes[b - 1].cx) ++cells;
+      ++b;
+    }
+    const uint32_t kp = (uint32_t)(b - a);
+    ++res->offsets;
+    if (kp > best_kp) { best_kp = kp; best_cells = cells; res->dx = votes[a].ox; res->dy = votes[a].oy; res->ties = 1; }
+    else if (kp == best_kp) ++res->ties; /* sorted by (oy, ox): the first one met stays */
+    a = b;
+  }
+  res->matched_keypoints = best_kp;
+  res->matched_cells = best_cells;
+  uint64_t l, r, t, bt;
+  ro_cell_limits(res->dx, pW, cW, &l, &r);
+  ro_cell_limits(res->dy, pH, cH, &t, &bt);
+  const uint32_t AW = cW / cell_w + 1, AH = cH / cell_h + 1;
+  uint8_t* act = (uint8_t*)calloc((size_t)AW * AH, 1);
+  for (size_t j = 0; j < nc; ++j) {
+    const uint64_t x = curr[j].x, y = curr[j].y;
+    if (!(x >= l && x < r && y >= t && y < bt)) continue;
+    const int64_t idx = (int64_t)pW * ((int64_t)y + res->dy) + ((int64_t)x + res->dx);
+    if (idx < 0 || idx >= (int64_t)pW * pH || pmask[idx] == 0) continue;
+    act[((y - t) / cell_h) * AW + (x - l) / cell_w] = 1;
+  }
+  for (size_t k = 0; k < (size_t)AW * AH; ++k) res->active_cells += act[k];
+  res->valid = !((float)res->matched_cells < (float)res->active_cells * 0.66f);
+  free(act); free(ps); free(votes);
+}
+size_t ro_sizeof_cell_match(void) { return sizeof(ro_cell_match_result); }
+
 size_t ro_sizeof_keypoint(void) { return sizeof(ro_keypoint); }
 size_t ro_sizeof_region_vote(void) { return sizeof(ro_region_vote); }
 size_t ro_sizeof_match_result(void) { return sizeof(ro_match_result); }

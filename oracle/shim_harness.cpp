@@ -18,7 +18,12 @@
 // and the results are compared: per fragment zero, dimensions, every dot histogram, the frame list; per
 // callback the fragment index, frame number, position and the fde::mask image.
 //
-// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1] [filter 0|1]     exit 0 = identical
+// With splice = 1 the reference's fragments are also spliced twice,
+//   fgs::splice        (src/fgs.hpp:187-213)     -- the reference, CPU
+//   fgs_b200::splice   (include/fgs_b200.hpp)    -- rb_snippet_create / rb_snippet_match on the GPU
+// and the resulting fragments compared (count, order, zero, dimensions, dots, frame lists).
+//
+// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1] [filter 0|1] [splice 0|1]   exit 0 = identical
 
 #include <algorithm>
 #include <chrono>
@@ -37,8 +42,10 @@
 #include "nic.hpp"
 
 #include "fdf.hpp"
+#include "fgs.hpp"
 
 #include "fdf_b200.hpp"
+#include "fgs_b200.hpp"
 #include "frc_b200.hpp"
 
 namespace {
@@ -156,6 +163,7 @@ int main(int argc, char** argv) {
   bool const fill = std::atoi(argv[6]) != 0;
   bool const gpu_blit = argc > 7 && std::atoi(argv[7]) != 0;
   bool const filter = argc > 8 && std::atoi(argv[8]) != 0;
+  bool const splice = argc > 9 && std::atoi(argv[9]) != 0;
   auto data = read_file(argv[1], w * h * n);
 
   std::vector<call_rec> ref_calls, gpu_calls;
@@ -213,6 +221,33 @@ int main(int argc, char** argv) {
     if (a.median != b.median) return fail("callback median", k);
     if (fill && !(a.keys == b.keys)) return fail("callback keys", k, a.keys.size());
     if (fill && a.weights != b.weights) return fail("callback weight counts", k);
+  }
+  if (splice) {
+    std::vector<fgm::fragment> ra, ga;
+    for (auto& f : ref_frags) { ra.push_back(f); ga.push_back(f); }
+    auto s0 = std::chrono::steady_clock::now();
+    auto rout = fgs::splice(ra.begin(), ra.end());
+    auto s1 = std::chrono::steady_clock::now();
+    std::size_t tied = 0;
+    fgs_b200::options sopt;
+    sopt.tied_matches = &tied;
+    auto gout = fgs_b200::splice(ga.begin(), ga.end(), sopt);
+    auto s2 = std::chrono::steady_clock::now();
+    if (rout.size() != gout.size()) return fail("splice: fragment count", rout.size(), gout.size());
+    for (std::size_t k = 0; k < rout.size(); ++k) {
+      auto& a = rout[k];
+      auto& b = gout[k];
+      if (!(a.zero() == b.zero())) return fail("splice: zero", k);
+      if (a.dots().width() != b.dots().width() || a.dots().height() != b.dots().height()) return fail("splice: dimensions", k);
+      if (std::memcmp(a.dots().data(), b.dots().data(), a.dots().size() * sizeof(fgm::dot_type)) != 0) return fail("splice: dots", k);
+      if (a.frames().size() != b.frames().size()) return fail("splice: frame count", k);
+      for (std::size_t j = 0; j < a.frames().size(); ++j)
+        if (a.frames()[j].number_ != b.frames()[j].number_ || !(a.frames()[j].position_ == b.frames()[j].position_))
+          return fail("splice: frame record", k, j);
+    }
+    std::printf("SPLICE IDENTICAL: %zu fragments -> %zu, %zu tied matches; fgs::splice %.1f ms, fgs_b200::splice %.1f ms\n",
+                ref_frags.size(), rout.size(), tied, std::chrono::duration<double, std::milli>(s1 - s0).count(),
+                std::chrono::duration<double, std::milli>(s2 - s1).count());
   }
   if (filter) {
     std::vector<fgm::fragment> frags;

@@ -24,6 +24,7 @@ SYMBOLS = [
     "rb_kernel_launches", "rb_device_bytes", "rb_last_error", "rb_abi_version", "rb_offsets_device",
     "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count", "rb_register_host_async", "rb_blit_blend",
     "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
+    "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
 ]
 
 
@@ -74,6 +75,16 @@ def load(build_if_missing: bool = False):
     lib.rb_blit_blend.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
     lib.rb_filter_fragment.restype = C.c_int
     lib.rb_filter_fragment.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.rb_snippet_create.restype = C.c_int
+    lib.rb_snippet_create.argtypes = [i32, vp, u32, u32, C.POINTER(vp)]
+    lib.rb_snippet_destroy.restype = None
+    lib.rb_snippet_destroy.argtypes = [vp]
+    lib.rb_snippet_last_error.restype = C.c_char_p
+    lib.rb_snippet_last_error.argtypes = [vp]
+    lib.rb_snippet_fetch.restype = C.c_int
+    lib.rb_snippet_fetch.argtypes = [vp, C.POINTER(u32), vp, vp, vp, sz]
+    lib.rb_snippet_match.restype = C.c_int
+    lib.rb_snippet_match.argtypes = [vp, vp, u32, u32, vp]
     lib.rb_upload_medians.restype = C.c_int
     lib.rb_upload_medians.argtypes = [vp, vp, sz, sz]
     lib.rb_filter_times.restype = C.c_int

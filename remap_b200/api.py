@@ -236,3 +236,63 @@ class Registrar:
     @property
     def device_bytes(self):
         return int(self._lib.rb_device_bytes(self._ctx))
+
+
+CELL_MATCH_DTYPE = np.dtype([("valid", "<u4"), ("dx", "<i4"), ("dy", "<i4"), ("matched_keypoints", "<u4"),
+                             ("matched_cells", "<u4"), ("active_cells", "<u4"), ("offsets", "<u4"), ("ties", "<u4"),
+                             ("pairs", "<u8")])
+
+
+class Snippet:
+    """fgs::details::extract_single (src/fgs.hpp:80-89) on the device: the blend of a fragment's dot map and the
+    keypoints of kpe with a 1 x 1 grid over the whole map image.  dots: (H, W, 16) uint16."""
+
+    def __init__(self, dots, device=0):
+        self._lib = _lib.load()
+        dots = np.ascontiguousarray(dots, np.uint16)
+        assert dots.ndim == 3 and dots.shape[2] == 16
+        self.height, self.width = dots.shape[:2]
+        self._s = C.c_void_p()
+        rc = self._lib.rb_snippet_create(device, dots.ctypes.data_as(C.c_void_p), self.width, self.height, C.byref(self._s))
+        if rc != 0:
+            msg = self._lib.rb_snippet_last_error(self._s).decode() if self._s else "no CUDA device (no CPU fallback exists)"
+            self.close()
+            raise RemapError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            self._lib.rb_snippet_destroy(self._s)
+            self._s = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RemapError(rc, self._lib.rb_snippet_last_error(self._s).decode())
+
+    def fetch(self):
+        """-> dict(image, mask, kps (KEYPOINT_DTYPE, unordered))"""
+        n = C.c_uint32()
+        self._check(self._lib.rb_snippet_fetch(self._s, C.byref(n), None, None, None, 0))
+        image = np.zeros((self.height, self.width), np.uint8)
+        mask = np.zeros((self.height, self.width), np.uint8)
+        kps = np.zeros(n.value, KEYPOINT_DTYPE)
+        self._check(self._lib.rb_snippet_fetch(self._s, C.byref(n), image.ctypes.data_as(C.c_void_p),
+                                               mask.ctypes.data_as(C.c_void_p), kps.ctypes.data_as(C.c_void_p), len(kps)))
+        return dict(image=image, mask=mask, kps=kps)
+
+    def match(self, curr, cell=(15, 15)):
+        """The cellular kpm::match (src/kpm.hpp:371-393) with self as `previous`.  -> CELL_MATCH_DTYPE record"""
+        res = np.zeros(1, CELL_MATCH_DTYPE)
+        self._check(self._lib.rb_snippet_match(self._s, curr._s, cell[0], cell[1], res.ctypes.data_as(C.c_void_p)))
+        return res[0]

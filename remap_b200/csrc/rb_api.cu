@@ -10,6 +10,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/remap_b200.h"
 #include "rb_host.hpp"
@@ -20,6 +21,7 @@
 #include "rb_prep.cuh"
 #include "rb_blit.cuh"
 #include "rb_fg.cuh"
+#include "rb_splice.cuh"
 
 static_assert(sizeof(rb_region_vote) == sizeof(RbRegionVote), "ABI mirror of RbRegionVote");
 static_assert(sizeof(rb_bin) == sizeof(RbBin), "ABI mirror of RbBin");
@@ -1370,6 +1372,221 @@ int rb_filter_times(rb_ctx* c, float* ms, size_t n, uint32_t* frames_deferred) {
   if (!c || !c->fg_ready) return RB_ERR_STATE;
   for (size_t i = 0; i < n && i < 3; ++i) ms[i] = c->fg_ms[i];
   if (frames_deferred) *frames_deferred = c->fg_last_deferred;
+  return RB_OK;
+}
+
+// ---- fragment splicing: fgs::details::extract_single + the cellular kpm::match ----------
+struct rb_snippet {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  RbGeom g;
+  uint8_t* d_image;   // blend image, g.pitch bytes per row
+  uint8_t* d_mask;    // blend mask, W bytes per row
+  uint32_t* d_kp;
+  uint32_t* d_w2;
+  RbSnipKp* d_kps;
+  uint32_t nkp;
+  unsigned long long* d_count;
+  std::string err;
+};
+
+#define RS_CUDA(s, call)                                                                        \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (s)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return RB_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+void rb_snippet_destroy(rb_snippet* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
+  cudaFree(s->d_image); cudaFree(s->d_mask); cudaFree(s->d_kp); cudaFree(s->d_w2); cudaFree(s->d_kps); cudaFree(s->d_count);
+  delete s;
+}
+
+const char* rb_snippet_last_error(rb_snippet* s) { return s ? s->err.c_str() : "null snippet"; }
+
+int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, rb_snippet** out) {
+  if (!dots || !out) return RB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return RB_ERR_NO_DEVICE;  // no CPU fallback
+  }
+  rb_snippet* s = new (std::nothrow) rb_snippet();
+  if (!s) return RB_ERR_INVALID;
+  *out = s;
+  s->device = device;
+  // kpe::extractor<kpr::grid<1, 1>, 0> (src/fgs.hpp:16,85): one region, no overlap
+  if (rb_make_geom(W, H, 1, 1, 0, 10, 3, &s->g) != 0 || W >= 32768 || H >= 32768) { s->err = "unsupported map size"; return RB_ERR_INVALID; }
+  const RbGeom& g = s->g;
+  RS_CUDA(s, cudaSetDevice(device));
+  RS_CUDA(s, cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
+  RS_CUDA(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  const size_t px = (size_t)W * H, words = (size_t)H * g.NS;
+  uint16_t* d_dots = nullptr;
+  RS_CUDA(s, cudaMalloc(&d_dots, px * 32));
+  RS_CUDA(s, cudaMalloc(&s->d_image, g.frame_stride + 256));
+  RS_CUDA(s, cudaMalloc(&s->d_mask, px + 256));
+  RS_CUDA(s, cudaMalloc(&s->d_kp, words * 4));
+  RS_CUDA(s, cudaMalloc(&s->d_w2, words * 4));
+  RS_CUDA(s, cudaMalloc(&s->d_count, 64));
+  RS_CUDA(s, cudaMemsetAsync(s->d_image, 0, g.frame_stride + 256, s->stream));
+  RS_CUDA(s, cudaMemsetAsync(s->d_kp, 0, words * 4, s->stream));
+  RS_CUDA(s, cudaMemsetAsync(s->d_w2, 0, words * 4, s->stream));
+  RS_CUDA(s, cudaMemsetAsync(s->d_count, 0, 64, s->stream));
+  RS_CUDA(s, cudaMemcpyAsync(d_dots, dots, px * 32, cudaMemcpyHostToDevice, s->stream));
+  // fragment.blend() (src/fgs.hpp:81, src/fgm.hpp:115-135)
+  rb_blend_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(d_dots, W, H, s->d_image, g.pitch, s->d_mask);
+  RS_CUDA(s, cudaGetLastError());
+  // extractor.extract(image, median, ...) (src/fgs.hpp:85-88): K1 on the one map image, no median output
+  RbKpeParams p;
+  p.g = g;
+  p.frames = s->d_image; p.median = nullptr; p.kpbits = s->d_kp; p.w2bits = s->d_w2; p.nframes = 1;
+  uint32_t nseg = (g.H - 6) / 8;  // a single image: as many row segments as the 4-row warm-up allows
+  if (nseg > 64) nseg = 64;
+  if (nseg < 1) nseg = 1;
+  p.nseg = nseg;
+  p.seg_rows = (g.H - 6 + nseg - 1) / nseg;
+  const size_t items = (size_t)nseg * g.NS;
+  rb_kpe_kernel<<<(uint32_t)((items + 127) / 128), 128, 0, s->stream>>>(p);
+  RS_CUDA(s, cudaGetLastError());
+  rb_count_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(s->d_kp, words, s->d_count);
+  RS_CUDA(s, cudaGetLastError());
+  unsigned long long n = 0;
+  RS_CUDA(s, cudaMemcpyAsync(&n, s->d_count, 8, cudaMemcpyDeviceToHost, s->stream));
+  RS_CUDA(s, cudaStreamSynchronize(s->stream));
+  cudaFree(d_dots);
+  s->nkp = (uint32_t)n;
+  RS_CUDA(s, cudaMalloc(&s->d_kps, ((size_t)n + 1) * sizeof(RbSnipKp)));
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(s->d_count + 1);
+  rb_snip_emit_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(g, s->d_image, s->d_kp, s->d_w2, s->d_kps, s->nkp, cnt);
+  RS_CUDA(s, cudaGetLastError());
+  RS_CUDA(s, cudaStreamSynchronize(s->stream));
+  return RB_OK;
+}
+
+int rb_snippet_fetch(rb_snippet* s, uint32_t* nkeypoints, uint8_t* out_image, uint8_t* out_mask, rb_keypoint* out_kps, size_t cap) {
+  if (!s) return RB_ERR_INVALID;
+  const RbGeom& g = s->g;
+  RS_CUDA(s, cudaSetDevice(s->device));
+  if (nkeypoints) *nkeypoints = s->nkp;
+  if (out_image) RS_CUDA(s, cudaMemcpy2DAsync(out_image, g.W, s->d_image, g.pitch, g.W, g.H, cudaMemcpyDeviceToHost, s->stream));
+  if (out_mask) RS_CUDA(s, cudaMemcpyAsync(out_mask, s->d_mask, (size_t)g.W * g.H, cudaMemcpyDeviceToHost, s->stream));
+  std::vector<RbSnipKp> h;
+  if (out_kps && s->nkp) {
+    h.resize(s->nkp);
+    RS_CUDA(s, cudaMemcpyAsync(h.data(), s->d_kps, (size_t)s->nkp * sizeof(RbSnipKp), cudaMemcpyDeviceToHost, s->stream));
+  }
+  RS_CUDA(s, cudaStreamSynchronize(s->stream));
+  for (size_t i = 0; i < h.size() && i < cap; ++i) {  // parity tap: the reference's 13-byte layout (src/kpe.hpp:342-379)
+    uint8_t v[25];
+    for (int n = 0; n < 25; ++n) v[n] = (h[i].c[n >> 3] >> (4 * (n & 7))) & 15;
+    const uint32_t weight = (h[i].c[3] >> 4) & 3;
+    rb_keypoint& k = out_kps[i];
+    memset(&k, 0, sizeof(k));
+    auto at = [&](int r, int c) { return v[5 * r + c]; };
+    k.code[0] = at(0, 0) | (at(0, 1) << 4);  k.code[1] = at(0, 2) | (at(0, 3) << 4);
+    k.code[2] = at(1, 0) | (at(0, 4) << 4);  k.code[3] = at(1, 1) | (at(1, 2) << 4);
+    k.code[4] = at(1, 3) | (at(1, 4) << 4);  k.code[5] = at(2, 0) | (at(2, 1) << 4);
+    k.code[6] = at(2, 2) | (at(2, 3) << 4);  k.code[7] = at(3, 0) | (at(2, 4) << 4);
+    k.code[8] = at(3, 1) | (at(3, 2) << 4);  k.code[9] = at(3, 3) | (at(3, 4) << 4);
+    k.code[10] = at(4, 0) | (at(4, 1) << 4); k.code[11] = at(4, 2) | (at(4, 3) << 4);
+    k.code[12] = (uint8_t)(weight | (at(4, 4) << 4));
+    k.weight = (uint8_t)weight;
+    k.x = (uint16_t)(h[i].xy & 0xFFFFu);
+    k.y = (uint16_t)(h[i].xy >> 16);
+    k.region_mask = 1;
+  }
+  return RB_OK;
+}
+
+// kpm::details::get_limits (src/kpm.hpp:301-315), size_t arithmetic included
+static void cell_limits(int32_t delta, uint64_t previous, uint64_t current, uint64_t* clo, uint64_t* chi) {
+  if (delta < 0) {
+    const uint64_t d = (uint64_t)(-(int64_t)delta);
+    *clo = d;
+    *chi = current < previous + d ? current : previous + d;
+  } else {
+    const uint64_t d = (uint64_t)delta;
+    *clo = 0;
+    *chi = current < previous - d ? current : previous - d;  // wraps like the reference when d > previous
+  }
+}
+
+int rb_snippet_match(rb_snippet* a, rb_snippet* b, uint32_t cell_w, uint32_t cell_h, rb_cell_match* out) {
+  if (!a || !b || !out || cell_w == 0 || cell_h == 0 || cell_w > 255 || cell_h > 255) return RB_ERR_INVALID;
+  memset(out, 0, sizeof(*out));
+  if (a->device != b->device) { a->err = "rb_snippet_match: snippets on different devices"; return RB_ERR_INVALID; }
+  if (a->nkp == 0 || b->nkp == 0) return RB_OK;  // count_offsets finds nothing: no vote (src/kpm.hpp:379-381)
+  RS_CUDA(a, cudaSetDevice(a->device));
+  cudaStream_t st = a->stream;
+  RS_CUDA(a, cudaStreamSynchronize(b->stream));
+  RbCellParams p;
+  memset(&p, 0, sizeof(p));
+  p.prev = a->d_kps; p.np = a->nkp; p.curr = b->d_kps; p.nc = b->nkp;
+  p.pW = a->g.W; p.pH = a->g.H; p.cW = b->g.W; p.cH = b->g.H;
+  p.nbuckets = next_pow2(2 * p.np < 1024 ? 1024 : 2 * p.np);
+  p.OW = p.pW + p.cW - 1; p.OH = p.pH + p.cH - 1;
+  p.cell_w = cell_w; p.cell_h = cell_h;
+  const size_t nbins = (size_t)p.OW * p.OH;
+  p.CW = (p.pW > p.cW ? p.pW : p.cW) / cell_w + 1;
+  const uint32_t CH = (p.pH > p.cH ? p.pH : p.cH) / cell_h + 1;
+  const size_t cellwords = ((size_t)p.CW * CH + 31) / 32;
+  p.AW = p.cW / cell_w + 1;
+  const size_t actwords = ((size_t)p.AW * (p.cH / cell_h + 1) + 31) / 32;
+  uint8_t* mem = nullptr;
+  const size_t bytes = ((size_t)p.nbuckets + p.np + nbins + cellwords + actwords) * 4 + 64;
+  RS_CUDA(a, cudaMalloc(&mem, bytes));
+  struct Free { uint8_t* m; ~Free() { cudaFree(m); } } guard{mem};
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(mem);
+  p.head = reinterpret_cast<uint32_t*>(mem + 64);
+  p.next = p.head + p.nbuckets;
+  p.hist = p.next + p.np;
+  p.cellbits = p.hist + nbins;
+  p.actbits = p.cellbits + cellwords;
+  RS_CUDA(a, cudaMemsetAsync(mem, 0, bytes, st));
+  RS_CUDA(a, cudaMemsetAsync(p.head, 0xFF, (size_t)p.nbuckets * 4, st));
+  const uint32_t grid = (uint32_t)a->sm_count * 8;
+  rb_cell_build_kernel<<<grid, 256, 0, st>>>(p);
+  rb_cell_vote_kernel<0><<<grid, 256, 0, st>>>(p);
+  rb_cell_best_kernel<<<grid, 256, 0, st>>>(p.hist, nbins, d_out);
+  RS_CUDA(a, cudaGetLastError());
+  unsigned long long h[8] = {0};
+  RS_CUDA(a, cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, st));
+  RS_CUDA(a, cudaStreamSynchronize(st));
+  out->offsets = (uint32_t)h[1];
+  out->pairs = h[2];
+  if (h[1] == 0) return RB_OK;  // no code in common
+  const uint32_t votes = (uint32_t)(h[0] >> 32), bin = 0xFFFFFFFFu - (uint32_t)(h[0] & 0xFFFFFFFFu);
+  p.best_dx = (int32_t)(bin % p.OW) - (int32_t)(p.cW - 1);
+  p.best_dy = (int32_t)(bin / p.OW) - (int32_t)(p.cH - 1);
+  // count_active_cells (src/kpm.hpp:349-369): the part of curr that prev covers at this offset
+  uint64_t l, r, t, bt;
+  cell_limits(p.best_dx, p.pW, p.cW, &l, &r);
+  cell_limits(p.best_dy, p.pH, p.cH, &t, &bt);
+  p.lim_l = (uint32_t)l; p.lim_r = (uint32_t)(r > 0xFFFFFFFFull ? 0xFFFFFFFFull : r);
+  p.lim_t = (uint32_t)t; p.lim_b = (uint32_t)(bt > 0xFFFFFFFFull ? 0xFFFFFFFFull : bt);
+  p.pmask = a->d_mask;
+  rb_cell_ties_kernel<<<grid, 256, 0, st>>>(p.hist, nbins, votes, d_out);
+  rb_cell_vote_kernel<1><<<grid, 256, 0, st>>>(p);
+  rb_cell_active_kernel<<<grid, 256, 0, st>>>(p);
+  rb_count_kernel<<<grid, 256, 0, st>>>(p.cellbits, cellwords, d_out + 4);
+  rb_count_kernel<<<grid, 256, 0, st>>>(p.actbits, actwords, d_out + 5);
+  RS_CUDA(a, cudaGetLastError());
+  RS_CUDA(a, cudaMemcpyAsync(h, d_out, 48, cudaMemcpyDeviceToHost, st));
+  RS_CUDA(a, cudaStreamSynchronize(st));
+  out->dx = p.best_dx; out->dy = p.best_dy;
+  out->matched_keypoints = votes;
+  out->ties = (uint32_t)h[3];
+  out->matched_cells = (uint32_t)h[4];
+  out->active_cells = (uint32_t)h[5];
+  out->valid = !((float)out->matched_cells < (float)out->active_cells * 0.66f);  // src/kpm.hpp:387-389
   return RB_OK;
 }
 

@@ -16,6 +16,7 @@
 #include "../../remap_b200/csrc/rb_kpe.cuh"
 #include "../../remap_b200/csrc/rb_prep.cuh"
 #include "../../remap_b200/csrc/rb_fg.cuh"
+#include "../../remap_b200/csrc/rb_splice.cuh"
 
 extern "C" {
 
@@ -180,6 +181,92 @@ int emul_fg(const uint8_t* frames, const uint8_t* medians, uint32_t n, uint32_t 
       if (!rbg::frame_body(p, s, i, RB_FG_NT)) ++deferred;
   }
   return deferred;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// Fragment splicing (rb_splice.cuh), item by item.  emul_snippet: dots (H*W*16 u16) -> blend image / mask and the
+// keypoint records of K1 with a 1 x 1 grid; returns the keypoint count.  recs: cap x 5 words (c[4], xy).
+int emul_snippet(const uint16_t* dots, uint32_t W, uint32_t H, uint8_t* image, uint8_t* mask, uint32_t* recs, uint32_t cap) {
+  RbKpeParams k;
+  if (rb_make_geom(W, H, 1, 1, 0, 10, 3, &k.g) != 0) return -1;
+  const RbGeom& g = k.g;
+  std::vector<uint8_t> dimg((size_t)g.frame_stride + 256, 0);
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t x = 0; x < W; ++x)
+      rbs::blend_pixel(dots + ((size_t)y * W + x) * 16, &dimg[(size_t)y * g.pitch + x], mask + (size_t)y * W + x);
+  for (uint32_t y = 0; y < H; ++y) memcpy(image + (size_t)y * W, &dimg[(size_t)y * g.pitch], W);
+  std::vector<uint32_t> kp((size_t)H * g.NS, 0), w2((size_t)H * g.NS, 0);
+  k.frames = dimg.data(); k.median = nullptr; k.kpbits = kp.data(); k.w2bits = w2.data(); k.nframes = 1;
+  uint32_t nseg = (H - 6) / 8;
+  if (nseg > 64) nseg = 64;
+  if (nseg < 1) nseg = 1;
+  k.nseg = nseg; k.seg_rows = (H - 6 + nseg - 1) / nseg;
+  for (uint32_t s = 0; s < nseg; ++s)
+    for (uint32_t j = 0; j < g.NS; ++j) rbk::kpe_strip(k, 0, s, j);
+  uint32_t count = 0;
+  for (uint32_t y = 0; y < H; ++y)
+    for (uint32_t j = 0; j < g.NS; ++j)
+      rbs::emit_word(g, dimg.data(), kp.data(), w2.data(), y, j, reinterpret_cast<RbSnipKp*>(recs), cap, &count);
+  return (int)count;
+}
+
+// The cellular match of two record lists; out = {valid, dx, dy, matched_keypoints, matched_cells, active_cells,
+// offsets, ties, pairs_lo, pairs_hi}.  The host steps between the kernels mirror rb_snippet_match.
+int emul_cell_match(const uint32_t* prev, uint32_t np, const uint8_t* pmask, uint32_t pW, uint32_t pH, const uint32_t* curr,
+                    uint32_t nc, uint32_t cW, uint32_t cH, uint32_t cell_w, uint32_t cell_h, uint32_t* out) {
+  memset(out, 0, 10 * 4);
+  if (np == 0 || nc == 0) return 0;
+  RbCellParams p;
+  memset(&p, 0, sizeof(p));
+  p.prev = reinterpret_cast<const RbSnipKp*>(prev); p.np = np;
+  p.curr = reinterpret_cast<const RbSnipKp*>(curr); p.nc = nc;
+  p.pW = pW; p.pH = pH; p.cW = cW; p.cH = cH;
+  p.nbuckets = 1024;
+  while (p.nbuckets < 2 * np) p.nbuckets <<= 1;
+  p.OW = pW + cW - 1; p.OH = pH + cH - 1;
+  p.cell_w = cell_w; p.cell_h = cell_h;
+  p.CW = (pW > cW ? pW : cW) / cell_w + 1;
+  const uint32_t CH = (pH > cH ? pH : cH) / cell_h + 1;
+  p.AW = cW / cell_w + 1;
+  std::vector<uint32_t> head(p.nbuckets, 0xFFFFFFFFu), next(np), hist((size_t)p.OW * p.OH, 0), cells(((size_t)p.CW * CH + 31) / 32, 0),
+      act(((size_t)p.AW * (cH / cell_h + 1) + 31) / 32, 0);
+  p.head = head.data(); p.next = next.data(); p.hist = hist.data(); p.cellbits = cells.data(); p.actbits = act.data();
+  for (uint32_t i = 0; i < np; ++i) rbs::build_item(p, i);
+  for (uint32_t j = 0; j < nc; ++j) rbs::vote_item<0>(p, j);
+  uint64_t best = 0, nz = 0, sum = 0;
+  for (size_t i = 0; i < hist.size(); ++i)
+    if (hist[i]) {
+      ++nz; sum += hist[i];
+      const uint64_t key = ((uint64_t)hist[i] << 32) | (0xFFFFFFFFu - (uint32_t)i);
+      if (key > best) best = key;
+    }
+  out[6] = (uint32_t)nz; out[8] = (uint32_t)sum; out[9] = (uint32_t)(sum >> 32);
+  if (!nz) return 0;
+  const uint32_t votes = (uint32_t)(best >> 32), bin = 0xFFFFFFFFu - (uint32_t)best;
+  p.best_dx = (int32_t)(bin % p.OW) - (int32_t)(cW - 1);
+  p.best_dy = (int32_t)(bin / p.OW) - (int32_t)(cH - 1);
+  auto limits = [](int32_t delta, uint64_t previous, uint64_t current, uint64_t* lo, uint64_t* hi) {
+    if (delta < 0) { const uint64_t d = (uint64_t)(-(int64_t)delta); *lo = d; *hi = current < previous + d ? current : previous + d; }
+    else { *lo = 0; *hi = current < previous - (uint64_t)delta ? current : previous - (uint64_t)delta; }
+  };
+  uint64_t l, r, t, b;
+  limits(p.best_dx, pW, cW, &l, &r);
+  limits(p.best_dy, pH, cH, &t, &b);
+  p.lim_l = (uint32_t)l; p.lim_r = (uint32_t)r; p.lim_t = (uint32_t)t; p.lim_b = (uint32_t)b;
+  p.pmask = pmask;
+  uint32_t ties = 0;
+  for (size_t i = 0; i < hist.size(); ++i) ties += hist[i] == votes;
+  for (uint32_t j = 0; j < nc; ++j) rbs::vote_item<1>(p, j);
+  for (uint32_t j = 0; j < nc; ++j) rbs::active_item(p, j);
+  uint32_t mc = 0, ac = 0;
+  for (uint32_t w : cells) mc += __builtin_popcount(w);
+  for (uint32_t w : act) ac += __builtin_popcount(w);
+  out[1] = (uint32_t)p.best_dx; out[2] = (uint32_t)p.best_dy; out[3] = votes; out[4] = mc; out[5] = ac; out[7] = ties;
+  out[0] = !((float)mc < (float)ac * 0.66f);
+  return 0;
 }
 
 }  // extern "C"

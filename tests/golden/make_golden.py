@@ -70,8 +70,35 @@ def filter_cases():
     yield "filter_noise", noisy
 
 
+def raw_splice_dump(frames):
+    N, H, W = frames.shape
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "f.bin"), os.path.join(td, "d.bin")
+        frames.tofile(fin)
+        subprocess.check_call([refdump.REF_BIN, "splice", fin, str(W), str(H), str(N), fout], stdout=subprocess.DEVNULL)
+        return np.fromfile(fout, np.uint8)
+
+
+def splice_cases():
+    """Fragment splicing (fgs::splice, src/fgs.hpp:187-213) fixtures: the reference's own collect, snippets,
+    pairwise cellular kpm::match and splice."""
+    yield "splice_levels", synth.scrolling_tilemap(60, 128, 96, seed=52, world_w=320, world_h=240, cut_every=15, levels=2).frames
+    yield "splice_repeat", synth.scrolling_tilemap(90, 128, 96, seed=53, world_w=512, world_h=384, cut_every=18, n_tiles=4,
+                                                   speckle=0.01).frames
+    yield "splice_chain", synth.scrolling_tilemap(120, 160, 112, seed=41, world_w=400, world_h=304, cut_every=30).frames
+
+
 def main():
     assert build_ref.build(), "needs /root/reference to build oracle/_ref"
+    for name, frames in splice_cases():
+        frames = np.ascontiguousarray(frames, np.uint8)
+        dump = raw_splice_dump(frames)
+        d = refdump.parse_splice_dump(dump.tobytes())
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), frames=frames, dump=dump)
+        print(name, frames.shape, "fragments", len(d["fragments"]), "->", len(d["spliced"]), "matches",
+              [(m["prev"], m["curr"], m["valid"], m["ties"]) for m in d["matches"]])
+    if "--splice-only" in sys.argv:
+        return
     for name, frames in filter_cases():
         frames = np.ascontiguousarray(frames, np.uint8)
         dump = raw_filter_dump(frames)

@@ -252,3 +252,44 @@ def test_foreground_body_against_reference_dump(name, golden_dir):
             for k, r in enumerate(recs):
                 assert np.array_equal(masks[k], r["mask"]), (name, fi, r["number"], general)
                 assert nkept[k] == len(r["contours"])
+
+
+# ---- fragment splicing (rb_splice.cuh) against the reference's dump of fgs snippets and cellular matches ----
+def emul_snippet(dots):
+    L = emul_build.lib()
+    H, W = dots.shape[:2]
+    d = np.ascontiguousarray(dots, np.uint16)
+    image = np.zeros((H, W), np.uint8)
+    mask = np.zeros((H, W), np.uint8)
+    recs = np.zeros((W * H, 5), np.uint32)
+    n = L.emul_snippet(P(d), W, H, P(image), P(mask), P(recs), len(recs))
+    assert n >= 0
+    return dict(image=image, mask=mask, recs=np.ascontiguousarray(recs[:n]))
+
+
+def emul_cell_match(a, b, cell=(15, 15)):
+    L = emul_build.lib()
+    out = np.zeros(10, np.uint32)
+    pm = np.ascontiguousarray(a["mask"])
+    assert L.emul_cell_match(P(a["recs"]), len(a["recs"]), P(pm), pm.shape[1], pm.shape[0], P(b["recs"]), len(b["recs"]),
+                             b["mask"].shape[1], b["mask"].shape[0], cell[0], cell[1], P(out)) == 0
+    s = out.astype(np.int64)
+    return dict(valid=int(s[0]), dx=int(out[1:2].view(np.int32)[0]), dy=int(out[2:3].view(np.int32)[0]), matched_keypoints=int(s[3]),
+                matched_cells=int(s[4]), active_cells=int(s[5]), offsets=int(s[6]), ties=int(s[7]), pairs=int(s[8] | (s[9] << 32)))
+
+
+@pytest.mark.parametrize("name", ["splice_levels", "splice_repeat", "splice_chain"])
+def test_splice_bodies_against_reference_dump(name, golden_dir):
+    import os
+    from oracle import refdump
+    from test_oracle_golden import check_cell_match
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    ref = refdump.parse_splice_dump(z["dump"].tobytes())
+    snips = [emul_snippet(f["dots"]) for f in ref["fragments"]]
+    for s, r in zip(snips, ref["snippets"]):
+        assert np.array_equal(s["mask"], r["mask"])
+        xy = s["recs"][:, 4]
+        order = np.lexsort((xy & 0xFFFF, xy >> 16))
+        assert np.array_equal((xy & 0xFFFF)[order], r["kps"]["x"]) and np.array_equal((xy >> 16)[order], r["kps"]["y"])
+    for m in ref["matches"]:
+        check_cell_match(emul_cell_match(snips[m["prev"]], snips[m["curr"]]), m, f"{name} {m['prev']}-{m['curr']}")

@@ -11,7 +11,7 @@ import parity
 from oracle import oracle, refdump
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not p.endswith("fgmask.npz") and not os.path.basename(p).startswith("filter_"))
+               if not p.endswith("fgmask.npz") and not os.path.basename(p).startswith(("filter_", "splice_")))
 
 
 def test_luts_known_answer():
@@ -121,3 +121,41 @@ def test_oracle_foreground_matches_reference_filter(name, golden_dir):
         out = oracle.filter_fragment(frames[idx], medians[idx], pos, mw, mh)
         assert np.array_equal(out["background"], bg), f"{name} fragment {fi}: background"
         assert np.array_equal(out["dots"], ref["fragments"][fi]["dots"]), f"{name} fragment {fi}: dots"
+
+
+# ---- fragment splicing: fgs::splice (src/fgs.hpp:187-213) ------------------------------------------------
+SPLICE_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "splice_*.npz")))
+
+
+def check_cell_match(got, want, what):
+    """got: record with the fields of oracle.CELL_MATCH_DTYPE; want: a match of refdump.parse_splice_dump."""
+    assert int(got["offsets"]) == want["offsets"] and int(got["pairs"]) == want["pairs"], what
+    assert int(got["ties"]) == want["ties"], what
+    if want["offsets"] == 0:
+        assert not got["valid"] and not want["valid"], what
+        return
+    assert int(got["matched_keypoints"]) == want["matched_keypoints"], what
+    if want["ties"] > 1:
+        return  # the reference's pick among tied offsets is std::unordered_map iteration order: not comparable
+    assert (int(got["dx"]), int(got["dy"])) == want["best"], what
+    assert int(got["matched_cells"]) == want["matched_cells"] and int(got["active_cells"]) == want["active_cells"], what
+    assert bool(got["valid"]) == want["valid"], what
+    if want["valid"]:
+        assert (int(got["dx"]), int(got["dy"])) == want["vote"] and int(got["matched_keypoints"]) == want["count"], what
+
+
+@pytest.mark.parametrize("name", SPLICE_CASES)
+def test_oracle_cell_match_matches_reference(name, golden_dir):
+    """The C restatement of fgs's snippets (blend + 1x1-grid kpe) and of the cellular kpm::match against the
+    real reference's dump of every snippet and every snippet pair."""
+    z = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    ref = refdump.parse_splice_dump(z["dump"].tobytes())
+    assert SPLICE_CASES and len(ref["fragments"]) >= 2
+    snips = [oracle.snippet(f["dots"]) for f in ref["fragments"]]
+    for s, r in zip(snips, ref["snippets"]):
+        order = np.lexsort((s["kps"]["x"], s["kps"]["y"]))
+        assert np.array_equal(s["mask"], r["mask"])
+        for fld in ("x", "y", "code"):
+            assert np.array_equal(s["kps"][fld][order], r["kps"][fld]), fld
+    for m in ref["matches"]:
+        check_cell_match(oracle.cell_match(snips[m["prev"]], snips[m["curr"]]), m, f"{name} {m['prev']}-{m['curr']}")
