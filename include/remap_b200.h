@@ -214,6 +214,14 @@ typedef struct rb_cell_match {
 } rb_cell_match;
 int rb_snippet_match(rb_snippet* prev, rb_snippet* curr, uint32_t cell_w, uint32_t cell_h, rb_cell_match* out);
 
+/* aws::details::compare (src/aws.hpp:37-60; called once per frame by aws::scan, :121) for every consecutive pair
+ * of the resident frames [first, first + n), in one streaming pass: heat (H*W bytes, in/out, may be NULL) is
+ * cleared wherever a pair differs, exactly as n - 1 compare calls leave it; first_change (H*W uint32, may be
+ * NULL) receives the index i of the first pair (first + i, first + i + 1) that differs at that pixel, 0xFFFFFFFF
+ * if none -- the heat map after k pairs is heat0 & (first_change >= k), so aws::scan's per-frame states can be
+ * replayed from one call.  (The context's width/height are the SCREEN dimensions here, src/aws.hpp:98-101.) */
+int rb_aws_compare(rb_ctx* ctx, size_t first, size_t n, uint8_t* heat, uint32_t* first_change);
+
 /* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
  * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */
 const rb_offset* rb_offsets_device(rb_ctx* ctx);

@@ -42,6 +42,7 @@ PATCHES = [
     ("kpe.hpp", "_mm256_castsi128_si256({})", "_mm256_castsi128_si256(_mm_setzero_si128())", 2),
     # unaligned buffers: MSVC emits unaligned moves for __m256i*, GCC does not.
     ("fde.hpp", "using mm_type = __m256i;", "using mm_type = __m256i_u;", 1),
+    ("aws.hpp", "using mm_t = __m256i;", "using mm_t = __m256i_u;", 1),
     # AVX-512VL/BW-only spelling of an unaligned 256-bit load; AVX2 spelling is identical.
     ("fde.hpp", "_mm256_loadu_epi8(bcur)",
      "_mm256_loadu_si256(reinterpret_cast<__m256i_u const*>(bcur))", 1),
@@ -52,7 +53,7 @@ PATCHES = [
 DEAD_MEMBER_RE = re.compile(
     r"\n  inline \[\[nodiscard\]\] __m256i get_unit(?:_low|_hi)?\(.*?\n  \}\n", re.S)
 
-FILES = ["all.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fdf.hpp", "fgm.hpp", "fgs.hpp",
+FILES = ["all.hpp", "aws.hpp", "cdt.hpp", "cpl.hpp", "cte.hpp", "ctr.hpp", "fde.hpp", "fdf.hpp", "fgm.hpp", "fgs.hpp",
          "frc.hpp", "icd.hpp", "ifd.hpp", "kpe.hpp", "kpm.hpp", "kpr.hpp", "mrl.hpp",
          "nic.hpp", "sid.hpp"]
 

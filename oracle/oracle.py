@@ -268,3 +268,17 @@ def cell_match(prev, curr, cell=(15, 15)):
     lib().ro_cell_match(_p(pk), len(pk), _p(pm), pm.shape[1], pm.shape[0], _p(ck), len(ck), curr["mask"].shape[1],
                         curr["mask"].shape[0], cell[0], cell[1], _p(res))
     return res[0]
+
+
+def aws_compare(frames, heat=None):
+    """aws::details::compare (src/aws.hpp:37-60) applied to every consecutive pair: heat &= (prev == curr).
+    -> (heat after all pairs, first_change (H, W) uint32: index of the first differing pair, 0xFFFFFFFF if none)"""
+    frames = np.asarray(frames, np.uint8)
+    N, H, W = frames.shape
+    h = np.ones((H, W), np.uint8) if heat is None else np.array(heat, np.uint8)
+    fc = np.full((H, W), 0xFFFFFFFF, np.uint32)
+    for i in range(N - 1):
+        ne = frames[i] != frames[i + 1]
+        fc[ne & (fc == 0xFFFFFFFF)] = i
+        h[ne] = 0
+    return h, fc

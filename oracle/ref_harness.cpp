@@ -18,6 +18,8 @@
 //                                           (src/fdf.hpp:40-91) over the collected fragments: dumps every
 //                                           frame's foreground contours and fde::mask, the backgrounds and
 //                                           the filtered fragments' dots; R > 1 repeats fdf::filter for timing
+//   heat  <frames.bin> W H N <out.bin>      aws::details::compare (src/aws.hpp:37-60) over every consecutive pair,
+//                                           from aws::scan's initial heat map of ones; dumps the map after each pair
 //   splice <frames.bin> W H N <out.bin>     frc::collector::collect + complete, then (a) every fragment as a
 //                                           fgs snippet (blend, kpe with a 1x1 grid, src/fgs.hpp:80-89) and the
 //                                           cellular kpm::match (src/kpm.hpp:371-393) of every snippet pair with
@@ -39,6 +41,7 @@
 #include <thread>
 #include <vector>
 
+#include "aws.hpp"
 #include "fde.hpp"
 #include "fdf.hpp"
 #include "fgs.hpp"
@@ -517,6 +520,27 @@ int run_splice(int argc, char** argv) {
   return 0;
 }
 
+int run_heat(int argc, char** argv) {
+  if (argc < 7) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  auto frames = read_file(argv[2], N * W * H);
+  FILE* out = std::fopen(argv[6], "wb");
+  if (!out) return 2;
+  mrl::dimensions_t const dim{W, H};
+  aws::heatmap_type heatmap{dim, {1}};  // src/aws.hpp:113
+  // padded copies: compare's vector loop runs to the 32-byte boundary past the image (src/aws.hpp:45-52)
+  sid::nat::dimg_t prev{dim}, cur{dim};
+  std::memcpy(prev.data(), frames.data(), W * H);
+  for (std::size_t i = 1; i < N; ++i) {
+    std::memcpy(cur.data(), frames.data() + i * W * H, W * H);
+    aws::details::compare(prev, cur, heatmap);
+    std::fwrite(heatmap.data(), 1, W * H, out);
+    std::swap(prev, cur);
+  }
+  std::fclose(out);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -527,5 +551,6 @@ int main(int argc, char** argv) {
   if (mode == "mask") return run_mask(argc, argv);
   if (mode == "filter") return run_filter(argc, argv);
   if (mode == "splice") return run_splice(argc, argv);
+  if (mode == "heat") return run_heat(argc, argv);
   return 1;
 }

@@ -234,3 +234,15 @@ def ref_splice(frames: np.ndarray) -> dict:
             d = parse_splice_dump(f.read())
     d["timing"] = json.loads(out.decode().strip().splitlines()[-1])
     return d
+
+
+def ref_heat(frames: np.ndarray) -> np.ndarray:
+    """aws::details::compare over consecutive pairs -> (N-1, H, W) heat maps after each pair (W*H % 32 == 0)."""
+    assert have_ref()
+    N, H, W = frames.shape
+    assert (W * H) % 32 == 0, "compare's vector loop runs to the next 32-byte boundary (src/aws.hpp:45-52)"
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "frames.bin"), os.path.join(td, "heat.bin")
+        np.ascontiguousarray(frames, np.uint8).tofile(fin)
+        subprocess.check_call([REF_BIN, "heat", fin, str(W), str(H), str(N), fout])
+        return np.fromfile(fout, np.uint8).reshape(N - 1, H, W)

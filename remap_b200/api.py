@@ -203,6 +203,15 @@ class Registrar:
                     times_ms=dict(background=ms[0], foreground=ms[1], masked_blit=ms[2]),
                     frames_deferred=int(deferred.value))
 
+    def aws_compare(self, n, first=0, heat=None):
+        """aws::details::compare (src/aws.hpp:37-60) over every consecutive pair of resident frames
+        [first, first + n).  heat: (H, W) uint8 to continue from, or None for aws::scan's initial map of ones
+        (src/aws.hpp:113).  -> (heat after all pairs, first_change (H, W) uint32)"""
+        h = np.ones((self.height, self.width), np.uint8) if heat is None else np.ascontiguousarray(heat, np.uint8).copy()
+        fc = np.zeros((self.height, self.width), np.uint32)
+        self._check(self._lib.rb_aws_compare(self._ctx, first, n, h.ctypes.data_as(C.c_void_p), fc.ctypes.data_as(C.c_void_p)))
+        return h, fc
+
     # -- introspection ------------------------------------------------------------------------
     @property
     def stream(self):

@@ -1590,4 +1590,41 @@ int rb_snippet_match(rb_snippet* a, rb_snippet* b, uint32_t cell_w, uint32_t cel
   return RB_OK;
 }
 
+// aws::details::compare (src/aws.hpp:37-60) for every consecutive pair of frames [first, first + n)
+int rb_aws_compare(rb_ctx* c, size_t first, size_t n, uint8_t* heat, uint32_t* first_change) {
+  if (!c || (!heat && !first_change)) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->uploaded) { c->err = "rb_aws_compare: frames not uploaded"; return RB_ERR_STATE; }
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const size_t px = (size_t)g.W * g.H, need = px * 5 + 256;
+  if (need > c->map_cap) {
+    if (c->d_map) { cudaFree(c->d_map); c->bytes -= c->map_cap; c->d_map = nullptr; }
+    c->map_cap = 0;
+    RB_CUDA(c, dmalloc(c, &c->d_map, need));
+    c->map_cap = need;
+  }
+  uint32_t* d_fc = reinterpret_cast<uint32_t*>(c->d_map);
+  uint8_t* d_heat = c->d_map + px * 4;
+  if (heat) RB_CUDA(c, cudaMemcpyAsync(d_heat, heat, px, cudaMemcpyHostToDevice, c->stream));
+  RB_CUDA(c, cudaMemsetAsync(d_fc, 0xFF, px * 4, c->stream));
+  if (n >= 2) {
+    const uint32_t total = (g.pitch / 16) * g.H, blocks = (total + 255) / 256;
+    // enough segments of the pair range to put ~4 waves of threads on the GPU, at least 8 pairs each
+    const uint64_t want = (uint64_t)c->sm_count * 2048 * 4;
+    uint32_t segs = (uint32_t)((want + total - 1) / total);
+    const uint32_t pairs = (uint32_t)n - 1;
+    if (segs > (pairs + 7) / 8) segs = (pairs + 7) / 8;
+    if (segs < 1) segs = 1;
+    const uint32_t seg_len = (pairs + segs - 1) / segs;
+    segs = (pairs + seg_len - 1) / seg_len;
+    rb_aws_compare_kernel<<<dim3(blocks, segs), 256, 0, c->stream>>>(c->d_frames + g.frame_stride * first, g.pitch, g.frame_stride,
+                                                                      g.W, g.H, (uint32_t)n, seg_len, heat ? d_heat : nullptr, d_fc);
+  }
+  RB_LAUNCHED(c, "rb_aws_compare_kernel");
+  if (heat) RB_CUDA(c, cudaMemcpyAsync(heat, d_heat, px, cudaMemcpyDeviceToHost, c->stream));
+  if (first_change) RB_CUDA(c, cudaMemcpyAsync(first_change, d_fc, px * 4, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
 }  // extern "C"

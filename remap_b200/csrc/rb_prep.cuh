@@ -183,3 +183,75 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
 }
 
 #endif  // __CUDACC__
+
+// ---- aws::details::compare (src/aws.hpp:37-60) over a run of resident frames ------------------------
+// The action-window scan ANDs "this pixel did not change" over consecutive frames into a heat map
+// (heat &= prev == curr, one call per frame, src/aws.hpp:121).  Here one pass over frames [0, n): a thread
+// owns 16 pixels, streams them through all n frames (each frame byte is read once, 128-bit loads) and
+// records the index of the FIRST pair that differs per pixel; heat after k pairs is then
+// first_change >= k, so the caller can replay the reference's per-frame states without another pass.
+// heat (in/out, 1 byte per pixel like aws::heatmap_type) is cleared where any pair differs;
+// first_change[p] = index i of the first pair (i, i + 1) with frame[i][p] != frame[i + 1][p], 0xFFFFFFFF if
+// none.  HBM-bound: 1 byte read per pixel and frame.
+RB_HD uint32_t rb_diff_bytes(uint32_t a, uint32_t b) {  // 0x80 in every byte that differs
+  const uint32_t v = a ^ b;
+  return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
+}
+
+#if defined(__CUDACC__)
+// blockIdx.y = segment of the pair range: pairs [seg * seg_len, (seg + 1) * seg_len); segments combine through
+// atomicMin on first_change (initialised to 0xFFFFFFFF by the caller), so a long run of frames fills the GPU
+// even though one frame has only a few thousand 16-pixel chunks.
+__global__ void __launch_bounds__(256) rb_aws_compare_kernel(const uint8_t* __restrict__ frames, uint32_t pitch, uint64_t frame_stride,
+                                                             uint32_t W, uint32_t H, uint32_t n, uint32_t seg_len,
+                                                             uint8_t* __restrict__ heat, uint32_t* __restrict__ first_change) {
+  const uint32_t chunks = pitch / 16, total = chunks * H;
+  const uint32_t i0 = blockIdx.y * seg_len;
+  const uint32_t i1 = i0 + seg_len < n - 1 ? i0 + seg_len : n - 1;  // pairs [i0, i1)
+  if (i0 >= i1) return;
+  for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < total; it += gridDim.x * blockDim.x) {
+    const uint32_t y = it / chunks, x = (it - y * chunks) * 16;
+    const uint8_t* src = frames + (uint64_t)y * pitch + x;
+    uint4 prev = __ldg(reinterpret_cast<const uint4*>(src + (uint64_t)i0 * frame_stride));
+    uint32_t fc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fc[k] = 0xFFFFFFFFu;
+    uint32_t seen[4] = {0, 0, 0, 0};  // bytes that have already changed
+    auto step = [&](const uint4& cur, uint32_t i) {
+      const uint32_t d[4] = {rb_diff_bytes(prev.x, cur.x), rb_diff_bytes(prev.y, cur.y), rb_diff_bytes(prev.z, cur.z),
+                             rb_diff_bytes(prev.w, cur.w)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t fresh = d[q] & ~seen[q];
+        if (fresh) {  // rare after the first few frames
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (fresh & (0x80u << (8 * b))) fc[4 * q + b] = i;
+          seen[q] |= fresh;
+        }
+      }
+      prev = cur;
+    };
+    uint32_t i = i0;
+    for (; i + 4 <= i1; i += 4) {  // four independent loads in flight
+      const uint8_t* q = src + (uint64_t)(i + 1) * frame_stride;
+      const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(q));
+      const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(q + frame_stride));
+      const uint4 c2 = __ldg(reinterpret_cast<const uint4*>(q + 2 * frame_stride));
+      const uint4 c3 = __ldg(reinterpret_cast<const uint4*>(q + 3 * frame_stride));
+      step(c0, i); step(c1, i + 1); step(c2, i + 2); step(c3, i + 3);
+    }
+    for (; i < i1; ++i) step(__ldg(reinterpret_cast<const uint4*>(src + (uint64_t)(i + 1) * frame_stride)), i);
+    if (seen[0] | seen[1] | seen[2] | seen[3]) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        if (x + k < W && fc[k] != 0xFFFFFFFFu) {
+          const uint64_t at = (uint64_t)y * W + x + k;
+          atomicMin(first_change + at, fc[k]);
+          if (heat) heat[at] = 0;
+        }
+      }
+    }
+  }
+}
+#endif

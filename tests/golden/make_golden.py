@@ -99,6 +99,15 @@ def main():
               [(m["prev"], m["curr"], m["valid"], m["ties"]) for m in d["matches"]])
     if "--splice-only" in sys.argv:
         return
+    # aws::details::compare (src/aws.hpp:37-60): a 96x64 "screen" with a static border around a scrolling window
+    seq = synth.scrolling_tilemap(12, 64, 40, seed=25, world_w=256, world_h=128)
+    screen = np.full((12, 64, 96), 6, np.uint8)
+    screen[:, 10:50, 16:80] = seq.frames
+    screen[5:, 2, 3] = 9           # a border pixel that changes once
+    np.savez_compressed(os.path.join(OUT, "awsheat.npz"), frames=screen, heat=refdump.ref_heat(screen))
+    print("awsheat ok")
+    if "--heat-only" in sys.argv:
+        return
     for name, frames in filter_cases():
         frames = np.ascontiguousarray(frames, np.uint8)
         dump = raw_filter_dump(frames)

@@ -15,7 +15,7 @@ from remap_b200 import RB_OFFSET_TIE_SENSITIVE, RB_OFFSET_VALID, synth
 pytestmark = pytest.mark.gpu
 
 GOLDEN = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not p.endswith("fgmask.npz") and not os.path.basename(p).startswith(("filter_", "splice_")))
+                if not p.endswith(("fgmask.npz", "awsheat.npz")) and not os.path.basename(p).startswith(("filter_", "splice_")))
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -361,3 +361,30 @@ def test_cooperative_declare_kernel_equals_the_one_thread_per_pair_reference():
         flagged = (outs[0]["flags"] & RB_OFFSET_TIE_SENSITIVE) != 0
         valid = (outs[0]["flags"] & RB_OFFSET_VALID) != 0
         assert valid.any() and (~valid).any() or not flagged.any()
+
+
+def test_aws_compare_matches_reference_and_oracle(golden_dir):
+    """rb_aws_compare (aws::details::compare over a run of frames) against the real reference's heat maps and,
+    on a screen-sized sequence, against the numpy restatement."""
+    z = np.load(os.path.join(golden_dir, "awsheat.npz"))
+    frames, ref = z["frames"], z["heat"]
+    n, H, W = frames.shape
+    with remap_b200.Registrar(W, H, max_frames=n) as reg:
+        reg.upload(frames)
+        heat, fc = reg.aws_compare(n)
+        assert np.array_equal(heat, ref[-1])
+        for k in range(len(ref)):
+            assert np.array_equal((fc > k).astype(np.uint8), ref[k]), k
+        h2, fc2 = reg.aws_compare(6, first=3, heat=ref[2])   # continue from a given map, sub-range
+        assert np.array_equal(h2, ref[7])
+    rng = np.random.default_rng(5)
+    seq = synth.scrolling_tilemap(300, 320, 224, seed=8)
+    screen = np.full((300, 312, 388), 14, np.uint8)          # the reference's screen size (src/main.cpp:194-244)
+    screen[:, 40:264, 32:352] = seq.frames
+    flick = rng.integers(0, 300, size=50)
+    screen[flick, rng.integers(0, 312, size=50), rng.integers(0, 388, size=50)] = 3
+    with remap_b200.Registrar(388, 312, max_frames=300) as reg:
+        reg.upload(screen)
+        heat, fc = reg.aws_compare(300)
+    oh, ofc = oracle.aws_compare(screen)
+    assert np.array_equal(heat, oh) and np.array_equal(fc, ofc)

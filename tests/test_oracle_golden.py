@@ -11,7 +11,7 @@ import parity
 from oracle import oracle, refdump
 
 CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-               if not p.endswith("fgmask.npz") and not os.path.basename(p).startswith(("filter_", "splice_")))
+               if not p.endswith(("fgmask.npz", "awsheat.npz")) and not os.path.basename(p).startswith(("filter_", "splice_")))
 
 
 def test_luts_known_answer():
@@ -159,3 +159,14 @@ def test_oracle_cell_match_matches_reference(name, golden_dir):
             assert np.array_equal(s["kps"][fld][order], r["kps"][fld]), fld
     for m in ref["matches"]:
         check_cell_match(oracle.cell_match(snips[m["prev"]], snips[m["curr"]]), m, f"{name} {m['prev']}-{m['curr']}")
+
+
+def test_oracle_aws_compare_matches_reference(golden_dir):
+    """numpy restatement of aws::details::compare against the real reference's heat map after every pair."""
+    z = np.load(os.path.join(golden_dir, "awsheat.npz"))
+    frames, ref = z["frames"], z["heat"]
+    heat, fc = oracle.aws_compare(frames)
+    assert np.array_equal(heat, ref[-1])
+    for k in range(len(ref)):  # the map after pair k is "no pair up to k differed"
+        assert np.array_equal((fc > k).astype(np.uint8), ref[k]), k
+    assert ref[-1][2, 3] == 0 and fc[2, 3] == 4 and ref[-1][0, 0] == 1
