@@ -156,6 +156,54 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def next_rows():
+    """Short measurements of the SURVEY.md 8(f) rows next to the hot path (N = 1 only, a few seconds): pass 2
+    (rb_filter_fragment = fdf::filter) on a 2,000-frame sprite sequence and one cellular kpm::match of two
+    1200x800 snippets (rb_snippet_match, fgs::splice).  Device-timed by the library's own CUDA events (filter)
+    and by wall clock around the synchronous call (match).  Informational; not part of the headline metric."""
+    import remap_b200
+    from remap_b200 import PLACEMENT_DTYPE, Snippet, shard, synth
+    out = {}
+    n, W, H = 2000, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=3, sprites=8)
+    with remap_b200.Registrar(W, H, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off, _ = reg.register(n)
+        pos = shard.positions(off)
+        idx = np.nonzero(pos[:, 0] == pos[0, 0])[0]
+        zx, zy, mw, mh = shard.fragment_extents(pos[idx, 1:], W, H)
+        pl = np.zeros(len(idx), PLACEMENT_DTYPE)
+        pl["frame"], pl["x"], pl["y"] = idx, pos[idx, 1] - zx, pos[idx, 2] - zy
+        best = None
+        for r in range(4):
+            res = reg.filter_fragment(pl, mw, mh, want_dots=False)
+            t = res["times_ms"]
+            if r and (best is None or sum(t.values()) < sum(best.values())):
+                best = t
+        tot = sum(best.values())
+        out["filter_fragment"] = {"replaces": "fdf::filter (src/fdf.hpp:40-75)", "frames": int(len(idx)),
+                                  "frames_per_s": len(idx) / (tot * 1e-3), "ms": {k: round(v, 3) for k, v in best.items()},
+                                  "contours_per_frame": float(res["ncontours"].mean()), "frames_deferred": res["frames_deferred"]}
+    rng = np.random.default_rng(7)
+    world = synth.make_world(rng, 2048, 1024, n_tiles=64, speckle=0.05)
+
+    def dots_of(img):
+        d = np.zeros(img.shape + (16,), np.uint16)
+        np.put_along_axis(d, img[:, :, None].astype(np.int64), 2, axis=2)
+        return d
+
+    with Snippet(dots_of(world[50:850, 100:1300])) as a, Snippet(dots_of(world[150:950, 500:1700])) as b:
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            m = a.match(b)
+            ts.append(time.perf_counter() - t0)
+        out["snippet_match"] = {"replaces": "kpm::match, cellular (src/kpm.hpp:371-393)", "map": [1200, 800],
+                                "pairs": int(m["pairs"]), "valid": int(m["valid"]), "offset": [int(m["dx"]), int(m["dy"])],
+                                "ms": round(min(ts[1:]) * 1e3, 3)}
+    return out
+
+
 def workload_config(args, kpf):
     c = {"workload": f"synthetic {args.width}x{args.height} scrolling tilemap (8x8 tiles, {args.speckle:.0%} speckle, "
                      f"seed {args.seed}), {args.frames} frames per GPU, kpe+kpm+declare",
@@ -182,6 +230,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4000, help="frames of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-next-rows", action="store_true", help="skip the short pass-2 / splicing measurements")
     ap.add_argument("--overlap-batches", type=int, default=0, help="rb_config.overlap_batches (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -372,6 +421,12 @@ def main():
             "config": workload_config(args, kpf), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "parity_ok": ok,
         }
+        if world == 1 and not args.no_next_rows:
+            try:
+                reg.close()  # free the 20,000-frame store first
+                line["next_rows"] = next_rows()
+            except Exception as e:  # informational: never lose the headline line over it
+                line["next_rows"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
         if not ok:
             print("ERROR: declared offsets differ from the generator's ground truth", file=sys.stderr)
