@@ -29,13 +29,20 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace fdf_b200 {
 
 struct options {
   int device{0};
+  bool callback{true};        // false: no per-frame callback at all (then nothing is decompressed either, see below)
   bool callback_masks{true};  // download every frame's fde::mask for the callback
+  // Resident mode: a context that still holds the frames AND their medians (frc_b200::collector with
+  // options::gpu_blit: collector.context(), collector.resident_numbers()).  Pass 2 then runs on the device
+  // store in place: no decompression, no upload; with callback = false the host only receives the dots.
+  rb_ctx* resident_ctx{nullptr};
+  std::vector<std::size_t> const* resident_numbers{nullptr};  // (*resident_numbers)[slot] = frame number
 };
 
 namespace details {
@@ -75,6 +82,11 @@ template<typename Comp, typename Callback>
   std::vector<fgm::fragment> results{};
   details::context dev;
   auto const pixels{frame_dim.area()};
+  bool const resident{opt.resident_ctx != nullptr && opt.resident_numbers != nullptr};
+  std::unordered_map<std::size_t, std::uint32_t> slot_of;
+  if (resident) {
+    for (std::size_t s{0}; s < opt.resident_numbers->size(); ++s) slot_of[(*opt.resident_numbers)[s]] = static_cast<std::uint32_t>(s);
+  }
 
   std::size_t i{0};
   for (auto& fragment : fragments) {
@@ -83,33 +95,57 @@ template<typename Comp, typename Callback>
     auto const map_dim{fragment.dots().dimensions()};
     auto const zero{fragment.zero()};
 
-    dev.ensure(frame_dim, n, opt.device);
+    rb_ctx* ctx{opt.resident_ctx};
+    if (!resident) {
+      dev.ensure(frame_dim, n, opt.device);
+      ctx = dev.ctx;
+    }
+    auto check{[&](int rc) {
+      if (rc != RB_OK) throw std::runtime_error(std::string{"fdf_b200::filter: "} + rb_last_error(ctx));
+    }};
     std::vector<sid::nat::dimg_t> images, medians;  // kept for the callback, as the reference hands them over
-    images.reserve(n);
-    medians.reserve(n);
     std::vector<rb_placement> places(n);
-    auto stage{static_cast<std::uint8_t*>(rb_alloc_host(2 * n * pixels + 16))};
-    if (stage == nullptr) throw std::runtime_error("fdf_b200::filter: rb_alloc_host failed");
+    std::uint8_t* stage{nullptr};
+    bool const unpack{!resident || opt.callback};  // somebody needs the frames on the host
+    if (unpack) {
+      images.reserve(n);
+      medians.reserve(n);
+    }
+    if (!resident) {
+      stage = static_cast<std::uint8_t*>(rb_alloc_host(2 * n * pixels + 16));
+      if (stage == nullptr) throw std::runtime_error("fdf_b200::filter: rb_alloc_host failed");
+    }
     auto mstage{stage + n * pixels};
     std::size_t k{0};
     for (auto& [no, pos, data] : frames) {  // src/fdf.hpp:58-60
-      images.push_back(comp(data.image_, frame_dim));
-      medians.push_back(comp(data.median_, frame_dim));
-      std::memcpy(stage + k * pixels, images.back().data(), pixels);
-      std::memcpy(mstage + k * pixels, medians.back().data(), pixels);
-      places[k] = {static_cast<std::uint32_t>(k), pos.x_ - zero.x_, pos.y_ - zero.y_};  // src/fgm.hpp:177
+      std::uint32_t slot{static_cast<std::uint32_t>(k)};
+      if (unpack) {
+        images.push_back(comp(data.image_, frame_dim));
+        medians.push_back(comp(data.median_, frame_dim));
+      }
+      if (resident) {
+        auto it{slot_of.find(no)};
+        if (it == slot_of.end()) throw std::runtime_error("fdf_b200::filter: frame not in the resident store");
+        slot = it->second;
+      }
+      else {
+        std::memcpy(stage + k * pixels, images.back().data(), pixels);
+        std::memcpy(mstage + k * pixels, medians.back().data(), pixels);
+      }
+      places[k] = {slot, pos.x_ - zero.x_, pos.y_ - zero.y_};  // src/fgm.hpp:177
       ++k;
     }
     fgm::fragment::matrix_type dots{map_dim};
-    std::vector<std::uint8_t> masks(opt.callback_masks ? n * pixels : 0);
-    if (n != 0) {
-      dev.check(rb_upload(dev.ctx, stage, 0, n));
-      dev.check(rb_upload_medians(dev.ctx, mstage, 0, n));
+    bool const want_masks{opt.callback && opt.callback_masks};
+    std::vector<std::uint8_t> masks(want_masks ? n * pixels : 0);
+    if (!resident && n != 0) {
+      check(rb_upload(ctx, stage, 0, n));
+      check(rb_upload_medians(ctx, mstage, 0, n));
     }
-    dev.check(rb_filter_fragment(dev.ctx, places.data(), n, static_cast<std::uint32_t>(map_dim.width_),
-                                 static_cast<std::uint32_t>(map_dim.height_), nullptr,
-                                 reinterpret_cast<std::uint16_t*>(dots.data()), nullptr, nullptr,
-                                 opt.callback_masks ? masks.data() : nullptr, nullptr));
+    check(rb_filter_fragment(ctx, places.data(), n, static_cast<std::uint32_t>(map_dim.width_),
+                             static_cast<std::uint32_t>(map_dim.height_), nullptr,
+                             reinterpret_cast<std::uint16_t*>(dots.data()), nullptr, nullptr,
+                             want_masks ? masks.data() : nullptr, nullptr));
     rb_free_host(stage);
 
     std::vector<fgm::frame> placed;  // what fragment::blit(pos, image, mask, no) records (src/fgm.hpp:84)
@@ -119,8 +155,9 @@ template<typename Comp, typename Callback>
 
     k = 0;
     for (auto& [no, pos, data] : frames) {  // src/fdf.hpp:66
+      if (!opt.callback) break;
       sid::mon::dimg_t mask{frame_dim};
-      if (opt.callback_masks) std::memcpy(mask.data(), masks.data() + k * pixels, pixels);
+      if (want_masks) std::memcpy(mask.data(), masks.data() + k * pixels, pixels);
       fdf::contours_t foreground{};
       cb(result, i, images[k], no, medians[k], pos, foreground, mask);
       ++k;

@@ -177,6 +177,7 @@ public:
         if (opt_.gpu_blit) { // same record as fragment::blit leaves (src/fgm.hpp:96), the dots come later
           pending_.emplace_back(no, position_, fgm::packed_data{comp(image), comp(median)});
           slots_.push_back(static_cast<std::uint32_t>(count_));
+          numbers_.push_back(no);
         }
         else {
           current_->blit(position_, image, {comp(image), comp(median)}, no); // src/frc.hpp:129-135
@@ -201,6 +202,16 @@ public:
 
   [[nodiscard]] inline fgm::fragment const& current() const noexcept {
     return *current_;
+  }
+
+  // gpu_blit only: the device context that still holds every collected frame and its median, and the frame
+  // number stored in each slot.  fdf_b200::filter can run pass 2 on them in place (fdf_b200::options::resident_*),
+  // without decompressing and uploading anything.  Valid while this collector lives.
+  [[nodiscard]] inline rb_ctx* context() const noexcept {
+    return ctx_;
+  }
+  [[nodiscard]] inline std::vector<std::size_t> const& resident_numbers() const noexcept {
+    return numbers_;
   }
 
   [[nodiscard]] inline std::list<fgm::fragment> complete() {
@@ -318,6 +329,7 @@ private:
   rb_offset* offsets_{nullptr};
   std::vector<std::uint8_t> carry_;
   std::vector<rb_keypoint> kps_;
+  std::vector<std::size_t> numbers_;  // gpu_blit: frame number held by each slot of the device store
 
   std::size_t count_{0};               // frames collected so far (== store slot with gpu_blit)
   std::vector<fgm::frame> pending_;    // gpu_blit: frames of the current fragment, dots still to come

@@ -35,6 +35,7 @@
 #include <limits>
 #include <list>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -177,16 +178,17 @@ int main(int argc, char** argv) {
     ref_frags = collector.complete();
   }
   auto t1 = std::chrono::steady_clock::now();
+  std::unique_ptr<frc_b200::collector> gcol;  // stays alive: filter = 2 runs pass 2 on its resident frames
   {
     frc_b200::options opt;
     opt.batch = batch;
     opt.fill_keys = fill;
     opt.gpu_blit = gpu_blit;
     opt.max_frames = n;
-    frc_b200::collector collector{mrl::dimensions_t{w, h}, opt};
+    gcol = std::make_unique<frc_b200::collector>(mrl::dimensions_t{w, h}, opt);
     memory_feed feed{data.data(), w, h, n};
-    collector.collect(feed, native_compression{}, recorder{&gpu_calls, fill});
-    gpu_frags = collector.complete();
+    gcol->collect(feed, native_compression{}, recorder{&gpu_calls, fill});
+    gpu_frags = gcol->complete();
   }
   auto t2 = std::chrono::steady_clock::now();
 
@@ -280,6 +282,22 @@ int main(int argc, char** argv) {
     std::printf("FILTER IDENTICAL: %zu fragments, %zu masks; fdf::filter %.1f ms, fdf_b200::filter %.1f ms\n", rout.size(),
                 rcalls.size(), std::chrono::duration<double, std::milli>(f1 - f0).count(),
                 std::chrono::duration<double, std::milli>(f2 - f1).count());
+    if (gpu_blit) {  // pass 2 in place on the frames the collector left on the device: no decompression, no upload
+      fdf_b200::options ropt;
+      ropt.callback = false;
+      ropt.resident_ctx = gcol->context();
+      ropt.resident_numbers = &gcol->resident_numbers();
+      std::vector<filter_rec> none;
+      auto f3 = std::chrono::steady_clock::now();
+      auto res = fdf_b200::filter(frags, mrl::dimensions_t{w, h}, native_compression{}, filter_recorder{&none}, ropt);
+      auto f4 = std::chrono::steady_clock::now();
+      if (res.size() != rout.size()) return fail("resident filter: fragment count", res.size(), rout.size());
+      for (std::size_t k = 0; k < rout.size(); ++k)
+        if (std::memcmp(rout[k].dots().data(), res[k].dots().data(), rout[k].dots().size() * sizeof(fgm::dot_type)) != 0)
+          return fail("resident filter: dots", k);
+      std::printf("RESIDENT FILTER IDENTICAL: %zu fragments; fdf_b200::filter on the collector's resident frames %.1f ms\n",
+                  res.size(), std::chrono::duration<double, std::milli>(f4 - f3).count());
+    }
     for (auto& f : frags) ref_frags.push_back(std::move(f));
   }
   std::printf("IDENTICAL: %zu fragments, %zu frames, %zu callbacks%s%s; reference %.1f ms, frc_b200 %.1f ms\n",

@@ -65,3 +65,11 @@ def test_filter_shim_matches_reference_fdf_filter(tmp_path):
     seq = synth.scrolling_tilemap(90, 320, 224, seed=21, sprites=6, cut_every=40)
     out = _run(seq.frames, 32, False, str(tmp_path), filter=True)
     assert "FILTER IDENTICAL" in out and "90 masks" in out, out
+
+
+def test_filter_shim_resident_mode(tmp_path):
+    """Pass 2 on the frames frc_b200::collector (gpu_blit) left on the device -- no decompression, no upload --
+    gives the reference's filtered dots too."""
+    seq = synth.scrolling_tilemap(90, 320, 224, seed=22, sprites=5, cut_every=40)
+    out = _run(seq.frames, 32, False, str(tmp_path), gpu_blit=True, filter=True)
+    assert "FILTER IDENTICAL" in out and "RESIDENT FILTER IDENTICAL" in out, out
