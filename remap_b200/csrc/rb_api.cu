@@ -1218,7 +1218,7 @@ static int fg_setup(rb_ctx* c) {
     const size_t avail = budget - fixed - 64;
     uint32_t scap = (uint32_t)(avail / 4 / 16);
     if (scap > 4096) scap = 4096;
-    size_t r = (avail - (size_t)scap * 16) * 8 / 17;  // 2 bytes label + 1 bit per run
+    size_t r = (avail - (size_t)scap * 16) * 4 / 9;  // 2 bytes label + 2 bits per run
     if (r > rmax) r = rmax;
     if (r + scap > 65535) r = 65535 - scap;
     r &= ~(size_t)31;

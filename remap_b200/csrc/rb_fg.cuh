@@ -72,7 +72,8 @@ struct RbFgWork {
   uint32_t* rowbase;   // [H]     run starts in the rows before this row
   uint32_t* misc;      // [0] R, [1] slots, [2] kept, [8..40) scan scratch
   L* parent;           // [rcap]
-  uint32_t* seedbits;  // [rcap / 32]
+  uint32_t* seedbits;  // [rcap / 32] roots that hold a seed
+  uint32_t* selbits;   // [rcap / 32] runs whose component holds a seed
   uint32_t* area;      // [scap]
   uint32_t* yl;        // [scap] first row << 16 | smallest column below the first row (0xFFFF: none)
   uint32_t* maxx;      // [scap]
@@ -86,7 +87,7 @@ RB_HD size_t fixed_bytes(uint32_t H, uint32_t NW) {  // bit maps + prefix tables
 }
 template <typename L>
 RB_HD size_t table_bytes(uint32_t rcap, uint32_t scap) {
-  return (size_t)rcap * sizeof(L) + ((size_t)rcap + 31) / 32 * 4 + (size_t)scap * 16 + 32;
+  return (size_t)rcap * sizeof(L) + ((size_t)rcap + 31) / 32 * 8 + (size_t)scap * 16 + 32;
 }
 
 // carve the fixed part out of `fix` and the tables out of `tab` (both 16-byte aligned)
@@ -101,7 +102,8 @@ RB_HD RbFgWork<L> carve(uint8_t* fix, uint8_t* tab, uint32_t H, uint32_t NW, uin
   s.misc = s.rowbase + H;
   s.base16 = reinterpret_cast<uint16_t*>(s.misc + 64);
   s.seedbits = reinterpret_cast<uint32_t*>(tab);
-  s.area = s.seedbits + (rcap + 31) / 32;
+  s.selbits = s.seedbits + (rcap + 31) / 32;
+  s.area = s.selbits + (rcap + 31) / 32;
   s.yl = s.area + scap;
   s.maxx = s.yl + scap;
   s.maxy = s.maxx + scap;
@@ -339,15 +341,41 @@ RB_HD void slot_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uint
   }
 }
 
+// Phase G2: bit k of selbits <=> run k belongs to a component that holds a seed.  One bit per thread, 32 runs
+// per warp and trip; the warp's bits leave as one word (ballot), no atomics.
+template <typename L>
+RB_HD void select_run(const RbFgWork<L>& s, uint32_t R, uint32_t k, bool on) {
+  bool bit = false;
+  if (on) {
+    const uint32_t r = s.parent[k];
+    bit = r >= R || ((s.seedbits[r >> 5] >> (r & 31)) & 1u);  // a seeded root already holds R + slot
+  }
+#if defined(__CUDA_ARCH__)
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, bit);
+  if ((threadIdx.x & 31) == 0 && (k >> 5) < (R + 31) / 32) s.selbits[k >> 5] = m;
+#else
+  if (bit) s.selbits[k >> 5] |= 1u << (k & 31);  // zeroed in phase C3
+#endif
+}
+
+// bits [k0, k0 + n) of selbits, n <= 33 (bit 32 is dropped: callers pass n <= 32 and treat run k0 + 32 separately)
+template <typename L>
+RB_HD uint32_t sel_range(const RbFgWork<L>& s, uint32_t k0, uint32_t n) {
+  const uint32_t lo = s.selbits[k0 >> 5] >> (k0 & 31);
+  const uint32_t hi = (k0 & 31) && ((k0 + n - 1) >> 5) != (k0 >> 5) ? s.selbits[(k0 >> 5) + 1] << (32 - (k0 & 31)) : 0u;
+  return (lo | hi) & low_mask(n - 1);
+}
+
 // Iterator over the run segments of one word: (run id k, first bit b, last bit e).
 struct RbFgSeg {
   uint32_t st, top, b, k;
+  uint32_t sel;  // bit j: the j-th segment from here on belongs to a seeded component
   bool more;
 };
 template <typename L>
 RB_HD RbFgSeg seg_begin(const RbFgParams& p, const RbFgWork<L>& s, uint32_t it, bool on) {
   RbFgSeg g;
-  g.st = g.top = g.b = g.k = 0;
+  g.st = g.top = g.b = g.k = g.sel = 0;
   g.more = false;
   if (!on) return g;
   const uint32_t y = it / p.NW, w = it - y * p.NW;
@@ -361,7 +389,11 @@ RB_HD RbFgSeg seg_begin(const RbFgParams& p, const RbFgWork<L>& s, uint32_t it, 
 #endif
   g.b = rb_ffs0(cols);
   g.k = s.rowbase[y] + s.base16[it] + rb_popc(g.st & low_mask(g.b)) - 1u;
-  g.more = true;
+  // the word's segments are runs g.k .. g.k + nseg - 1 (nseg <= 32: at most 31 starts after the first interior bit);
+  // words without a seeded run -- most of them -- are skipped whole
+  const uint32_t nseg = 1u + rb_popc(g.st & ~low_mask(g.b));
+  g.sel = sel_range(s, g.k, nseg);
+  g.more = g.sel != 0;
   return g;
 }
 RB_HD uint32_t seg_end(const RbFgSeg& g) {  // last bit of the current segment
@@ -369,7 +401,8 @@ RB_HD uint32_t seg_end(const RbFgSeg& g) {  // last bit of the current segment
   return higher ? rb_ffs0(higher) - 1u : g.top;
 }
 RB_HD void seg_next(RbFgSeg& g, uint32_t e) {
-  if (e >= g.top) { g.more = false; return; }
+  g.sel >>= 1;
+  if (e >= g.top || g.sel == 0) { g.more = false; return; }  // nothing seeded further right
   g.b = e + 1;
   ++g.k;
 }
@@ -382,8 +415,8 @@ RB_HD void stats_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uin
   while (RB_WARP_ANY(g.more)) {
     if (g.more) {
       const uint32_t e = seg_end(g);
-      const uint32_t slot = slot_of(s, R, g.k);
-      if (slot != RB_FG_NONE) {
+      if (g.sel & 1u) {
+        const uint32_t slot = slot_of(s, R, g.k);
         const uint32_t x0 = x32 + g.b, x1 = x32 + e;
         rb_atomic_add(s.area + slot, e - g.b + 1u);
         if (x1 > s.maxx[slot]) a_max(s.maxx + slot, x1);
@@ -404,29 +437,74 @@ RB_HD void paint_word(const RbFgParams& p, const RbFgWork<L>& s, uint32_t R, uin
   while (RB_WARP_ANY(g.more)) {
     if (g.more) {
       const uint32_t e = seg_end(g);
-      const uint32_t slot = slot_of(s, R, g.k);
-      if (slot != RB_FG_NONE && s.area[slot] <= p.area_limit) out |= low_mask(e) & ~(low_mask(g.b) >> 1);
+      if ((g.sel & 1u) && s.area[slot_of(s, R, g.k)] <= p.area_limit) out |= low_mask(e) & ~(low_mask(g.b) >> 1);
       seg_next(g, e);
     }
   }
   if (on) s.ev[it] = out;
 }
 
-// Phase J: lane `lane` of the warp that paints slot `slot`'s enclosure (src/fde.hpp:133-143).
+// Phase J: the enclosures of the kept components (src/fde.hpp:133-143).  Most contours are a few pixels, so
+// J1 gives every slot ONE lane that paints its rectangle if it has at most RB_FG_BOX_SMALL (row, word) items;
+// larger rectangles are queued (in the seed bit map's memory, dead since phase F) and painted by a whole warp
+// each in J2.  A full queue only costs time: the lane then paints its large rectangle itself.
+#define RB_FG_BOX_SMALL 16u
+
+struct RbFgBox {
+  uint32_t top, w0, nww, total, left, right;
+};
 template <typename L>
-RB_HD void box_lane(const RbFgParams& p, const RbFgWork<L>& s, uint32_t slot, uint32_t lane) {
-  if (s.area[slot] > p.area_limit) return;
-  if (lane == 0) rb_atomic_add(s.misc + 2, 1u);
-  const uint32_t top = s.yl[slot] >> 16, left = s.yl[slot] & 0xFFFFu, right = s.maxx[slot], bottom = s.maxy[slot];
-  if (left >= right || top >= bottom) return;  // left == 0xFFFF: single-row contour, nothing below the first row
-  const uint32_t w0 = left >> 5, w1 = (right - 1) >> 5, nww = w1 - w0 + 1, total = (bottom - top) * nww;
-  for (uint32_t j = lane; j < total; j += 32) {
-    const uint32_t y = top + j / nww, w = w0 + j % nww;
-    uint32_t m = 0xFFFFFFFFu;
-    if (w == w0) m &= ~(low_mask(left & 31) >> 1);           // bits >= left
-    if (w == w1 && (right & 31)) m &= low_mask((right & 31) - 1);  // bits < right
-    a_or(s.ev + y * p.NW + w, m);
+RB_HD RbFgBox box_of(const RbFgParams& p, const RbFgWork<L>& s, uint32_t slot) {
+  RbFgBox b;
+  b.top = s.yl[slot] >> 16;
+  b.left = s.yl[slot] & 0xFFFFu;  // 0xFFFF: single-row contour, nothing below the first row
+  b.right = s.maxx[slot];
+  const uint32_t bottom = s.maxy[slot];
+  b.w0 = b.left >> 5;
+  b.nww = 0; b.total = 0;
+  if (b.left < b.right && b.top < bottom) {
+    b.nww = ((b.right - 1) >> 5) - b.w0 + 1;
+    b.total = (bottom - b.top) * b.nww;
   }
+  return b;
+}
+template <typename L>
+RB_HD void box_item(const RbFgParams& p, const RbFgWork<L>& s, const RbFgBox& b, uint32_t j) {
+  const uint32_t y = b.top + j / b.nww, w = b.w0 + j % b.nww;
+  uint32_t m = 0xFFFFFFFFu;
+  if (w == b.w0) m &= ~(low_mask(b.left & 31) >> 1);                              // bits >= left
+  if (w == b.w0 + b.nww - 1 && (b.right & 31)) m &= low_mask((b.right & 31) - 1);  // bits < right
+  a_or(s.ev + y * p.NW + w, m);
+}
+
+template <typename L>
+RB_HD void box_small(const RbFgParams& p, const RbFgWork<L>& s, uint32_t slot, bool on, uint32_t qcap) {
+  RbFgBox b;
+  b.total = 0; b.nww = 1; b.top = b.w0 = b.left = b.right = 0;
+  const bool kept = on && s.area[slot] <= p.area_limit;
+#if defined(__CUDA_ARCH__)
+  const uint32_t nk = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, kept));
+  if ((threadIdx.x & 31) == 0 && nk) atomicAdd(s.misc + 2, nk);
+#else
+  if (kept) ++s.misc[2];
+#endif
+  if (kept) {
+    b = box_of(p, s, slot);
+    if (b.total > RB_FG_BOX_SMALL) {
+      const uint32_t at = rb_atomic_add(s.misc + 3, 1u);
+      if (at < qcap) { s.seed[at] = slot; b.total = 0; }
+    }
+  }
+  uint32_t j = 0;
+  while (RB_WARP_ANY(j < b.total)) {
+    if (j < b.total) { box_item(p, s, b, j); ++j; }
+  }
+}
+
+template <typename L>
+RB_HD void box_large_lane(const RbFgParams& p, const RbFgWork<L>& s, uint32_t slot, uint32_t lane) {
+  const RbFgBox b = box_of(p, s, slot);
+  for (uint32_t j = lane; j < b.total; j += 32) box_item(p, s, b, j);
 }
 
 // One frame through all phases.  Returns false (block-uniformly) when the frame does not fit the tables.
@@ -484,7 +562,7 @@ RB_HD bool frame_body(const RbFgParams& p, const RbFgWork<L>& s, uint32_t i, uin
       }
     }
     for (uint32_t k = tid; k < R; k += NT) s.parent[k] = (L)k;
-    for (uint32_t k = tid; k < (R + 31) / 32; k += NT) s.seedbits[k] = 0;
+    for (uint32_t k = tid; k < (R + 31) / 32; k += NT) { s.seedbits[k] = 0; s.selbits[k] = 0; }
   }
   RB_SYNC();
   // the item loops below run the same number of trips in every lane (see RB_WARP_ANY)
@@ -506,6 +584,10 @@ RB_HD bool frame_body(const RbFgParams& p, const RbFgWork<L>& s, uint32_t i, uin
   RB_SYNC();
   const uint32_t nslots = s.misc[1];
   if (nslots > p.scap) return false;
+  RB_FOR_THREADS(tid, NT) {  // G2: runs of seeded components
+    for (uint32_t base = 0; base < R; base += NT) select_run(s, R, base + tid, base + tid < R);
+  }
+  RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // H: statistics
     for (uint32_t base = 0; base < nwords; base += NT) stats_word(p, s, R, base + tid, base + tid < nwords);
   }
@@ -514,8 +596,13 @@ RB_HD bool frame_body(const RbFgParams& p, const RbFgWork<L>& s, uint32_t i, uin
     for (uint32_t base = 0; base < nwords; base += NT) paint_word(p, s, R, base + tid, base + tid < nwords);
   }
   RB_SYNC();
-  RB_FOR_THREADS(tid, NT) {  // J: enclosures
-    for (uint32_t slot = tid / 32; slot < nslots; slot += NT / 32) box_lane(p, s, slot, tid & 31);
+  RB_FOR_THREADS(tid, NT) {  // J1: small enclosures, one lane each
+    for (uint32_t base = 0; base < nslots; base += NT) box_small(p, s, base + tid, base + tid < nslots, nwords);
+  }
+  RB_SYNC();
+  const uint32_t nlarge = s.misc[3] < nwords ? s.misc[3] : nwords;
+  RB_FOR_THREADS(tid, NT) {  // J2: large enclosures, one warp each
+    for (uint32_t q = tid / 32; q < nlarge; q += NT / 32) box_large_lane(p, s, s.seed[q], tid & 31);
   }
   RB_SYNC();
   RB_FOR_THREADS(tid, NT) {  // K: out
