@@ -161,6 +161,15 @@ typedef struct rb_placement {
 int rb_blit_blend(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_t mapW, uint32_t mapH, uint16_t* out_dots,
                   uint8_t* out_image, uint8_t* out_mask);
 
+/* Multi-GPU map assembly (per-rank partial dot maps, one reduction to rank 0, blend there).
+ * Every rank calls rb_blit_blend (or rb_filter_fragment) with ITS frames and the fragment's full map geometry;
+ * rb_map_device hands out the device addresses of the result so that the partial dot maps can be summed across
+ * ranks in place (NCCL reduce; uint16 counters wrap, so sum in a wider type and keep the low 16 bits --
+ * remap_b200.shard.reduce_fragment_map does); rb_blend_map then runs fgm::fragment::blend (src/fgm.hpp:115-135)
+ * over the reduced dots on the destination rank.  Pointers stay valid until the context's next map call. */
+int rb_map_device(rb_ctx* ctx, uint16_t** dots, uint8_t** image, uint8_t** mask, uint32_t* mapW, uint32_t* mapH);
+int rb_blend_map(rb_ctx* ctx, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask);
+
 /* Pass-2 foreground filtering of one fragment: fdf::filter (src/fdf.hpp:40-75).  For every
  * placed frame: fde::extractor::extract (src/fde.hpp:83-103: generate_mask against the background window, the
  * contours of the frame's MEDIAN image that hold a differing pixel -- cte::extractor, src/cte.hpp:60-166 --

@@ -203,6 +203,26 @@ class Registrar:
                     times_ms=dict(background=ms[0], foreground=ms[1], masked_blit=ms[2]),
                     frames_deferred=int(deferred.value))
 
+    def map_device(self):
+        """Device addresses of the map the last blit_blend / filter_fragment left in the context's scratch.
+        -> dict(dots, image, mask (ints), width, height)"""
+        d, i, m = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        w, h = C.c_uint32(), C.c_uint32()
+        self._check(self._lib.rb_map_device(self._ctx, C.byref(d), C.byref(i), C.byref(m), C.byref(w), C.byref(h)))
+        return dict(dots=d.value, image=i.value, mask=m.value, width=w.value, height=h.value)
+
+    def blend_map(self, want_dots=True):
+        """fgm::fragment::blend over the dots currently in the map scratch (after a cross-rank reduction).
+        -> (dots | None, image, mask)"""
+        md = self.map_device()
+        h, w = md["height"], md["width"]
+        dots = np.zeros((h, w, 16), np.uint16) if want_dots else None
+        image = np.zeros((h, w), np.uint8)
+        mask = np.zeros((h, w), np.uint8)
+        self._check(self._lib.rb_blend_map(self._ctx, dots.ctypes.data_as(C.c_void_p) if want_dots else None,
+                                           image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
+        return dots, image, mask
+
     def aws_compare(self, n, first=0, heat=None):
         """aws::details::compare (src/aws.hpp:37-60) over every consecutive pair of resident frames
         [first, first + n).  heat: (H, W) uint8 to continue from, or None for aws::scan's initial map of ones

@@ -332,6 +332,7 @@ struct rb_ctx {
   size_t places_cap;
   uint8_t* d_map;         // dots (32 B / map pixel) + image + mask
   size_t map_cap;
+  uint32_t map_w, map_h;  // geometry of the map the scratch holds (last rb_blit_blend / rb_filter_fragment)
   uint8_t* d_bg;       // scratch for rb_foreground_mask
   size_t bg_cap;
   uint8_t* d_fgframe;  // dense frame scratch
@@ -1139,6 +1140,7 @@ int rb_blit_blend(rb_ctx* c, const rb_placement* placements, size_t n, uint32_t 
   uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
   uint8_t* d_img = c->d_map + px * 32;
   uint8_t* d_msk = d_img + px;
+  c->map_w = mapW; c->map_h = mapH;
   if (n) RB_CUDA(c, cudaMemcpyAsync(c->d_places, placements, n * sizeof(RbPlacement), cudaMemcpyHostToDevice, c->stream));
   const dim3 grid((mapW + RB_BLIT_TX - 1) / RB_BLIT_TX, (mapH + RB_BLIT_TY - 1) / RB_BLIT_TY);
   rb_blit_blend_kernel<false><<<grid, RB_BLIT_NT, 0, c->stream>>>(c->d_frames, g.pitch, g.frame_stride, g.W, g.H, c->d_places,
@@ -1305,6 +1307,7 @@ int rb_filter_fragment(rb_ctx* c, const rb_placement* placements, size_t n, uint
   uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
   uint8_t* d_img = c->d_map + px * 32;
   uint8_t* d_msk = d_img + px;
+  c->map_w = mapW; c->map_h = mapH;
   const dim3 grid((mapW + RB_BLIT_TX - 1) / RB_BLIT_TX, (mapH + RB_BLIT_TY - 1) / RB_BLIT_TY);
   if (n) RB_CUDA(c, cudaMemcpyAsync(c->d_places, placements, n * sizeof(RbPlacement), cudaMemcpyHostToDevice, c->stream));
   RB_CUDA(c, cudaEventRecord(c->fg_ev[0], c->stream));
@@ -1623,6 +1626,37 @@ int rb_aws_compare(rb_ctx* c, size_t first, size_t n, uint8_t* heat, uint32_t* f
   RB_LAUNCHED(c, "rb_aws_compare_kernel");
   if (heat) RB_CUDA(c, cudaMemcpyAsync(heat, d_heat, px, cudaMemcpyDeviceToHost, c->stream));
   if (first_change) RB_CUDA(c, cudaMemcpyAsync(first_change, d_fc, px * 4, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+// Multi-GPU map assembly: the device addresses of the map the scratch holds, and blend over dots that the
+// caller has reduced across ranks in place.
+int rb_map_device(rb_ctx* c, uint16_t** dots, uint8_t** image, uint8_t** mask, uint32_t* mapW, uint32_t* mapH) {
+  if (!c) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_map_device: no map assembled yet"; return RB_ERR_STATE; }
+  const size_t px = (size_t)c->map_w * c->map_h;
+  if (dots) *dots = reinterpret_cast<uint16_t*>(c->d_map);
+  if (image) *image = c->d_map + px * 32;
+  if (mask) *mask = c->d_map + px * 33;
+  if (mapW) *mapW = c->map_w;
+  if (mapH) *mapH = c->map_h;
+  return RB_OK;
+}
+
+int rb_blend_map(rb_ctx* c, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask) {
+  if (!c) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_blend_map: no map assembled yet"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const size_t px = (size_t)c->map_w * c->map_h;
+  uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
+  uint8_t* d_img = c->d_map + px * 32;
+  uint8_t* d_msk = d_img + px;
+  rb_blend_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_dots, c->map_w, c->map_h, d_img, c->map_w, d_msk);
+  RB_LAUNCHED(c, "rb_blend_kernel");
+  if (out_dots) RB_CUDA(c, cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
+  if (out_mask) RB_CUDA(c, cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RB_OK;
 }

@@ -122,3 +122,41 @@ def _round_up_step(change: int, step: int) -> int:
     """fgm::fragment::get_step (src/fgm.hpp:228-233)"""
     rest = change % step
     return (change - rest) + (step if rest else 0)
+
+
+class _DeviceArray:
+    """A raw device allocation as something torch.as_tensor understands (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def reduce_fragment_map(reg, group=None, dst: int = 0):
+    """Multi-GPU map assembly.  Every rank has called ``reg.blit_blend`` (or
+    ``reg.filter_fragment``) with ITS frames of one fragment and the fragment's full map geometry; this sums the
+    partial dot maps to rank ``dst`` with one reduction (NCCL over NVLink on GPUs; through host memory when the
+    process group is gloo, as in the single-GPU tests) and runs ``fgm::fragment::blend`` there.
+
+    The reference's counters are uint16 and wrap (src/fgm.hpp:12-14,94): the partial maps wrap the same way,
+    so they are summed as int32 and only the low 16 bits are kept -- equal to one wrapping counter over all frames.
+    -> (dots, image, mask) on rank ``dst``, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    md = reg.map_device()
+    count = md["width"] * md["height"] * 16
+    dev = torch.device("cuda", torch.cuda.current_device())
+    part16 = torch.as_tensor(_DeviceArray(md["dots"], count, "<i2"), device=dev)   # view, not a copy
+    wide = part16.to(torch.int32) & 0xFFFF
+    if dist.get_backend(group) == "nccl":
+        dist.reduce(wide, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    else:
+        host = wide.cpu()
+        dist.reduce(host, dst=dst, op=dist.ReduceOp.SUM, group=group)
+        wide = host.to(dev)
+    if dist.get_rank(group) != dst:
+        return None
+    low = wide & 0xFFFF
+    part16.copy_((((low + 0x8000) & 0xFFFF) - 0x8000).to(torch.int16))  # same bits as the uint16 value
+    torch.cuda.current_stream().synchronize()
+    return reg.blend_map()
