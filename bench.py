@@ -153,7 +153,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def next_rows():
@@ -216,7 +216,27 @@ def workload_config(args, kpf):
     return c
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (this
+    image sets NCCL_DEBUG=VERSION, so NCCL prints its banner there): from here on fd 1 is stderr, and the JSON
+    line goes to a private duplicate of the real stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -427,7 +447,7 @@ def main():
                 line["next_rows"] = next_rows()
             except Exception as e:  # informational: never lose the headline line over it
                 line["next_rows"] = {"error": str(e)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
         if not ok:
             print("ERROR: declared offsets differ from the generator's ground truth", file=sys.stderr)
     reg.close()
