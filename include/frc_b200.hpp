@@ -58,6 +58,13 @@ struct options {
   // fragment handed to the callback has its frames but not yet its dots.
   bool gpu_blit{false};
   std::size_t max_frames{0};  // capacity of the frame store with gpu_blit
+  // gpu_blit only.  false: the frame records carry no compressed image / median (fgm::packed_data stays empty):
+  // the frames and medians live on in the device store, where fdf_b200::filter's resident mode finds them.  The
+  // two comp() calls per frame (src/frc.hpp:134) are what the host spends most of its time on otherwise.
+  bool keep_packed{true};
+  // false: medians are not copied back, the callback receives a zeroed median image (the reference's callback
+  // only writes it to a PNG when asked to, src/main.cpp:139-149).
+  bool fetch_medians{true};
 };
 
 class collector {
@@ -149,14 +156,16 @@ public:
         throw std::runtime_error("frc_b200::collector: sequence longer than options::max_frames (gpu_blit)");
       }
       check(rb_upload(ctx_, stage_ + skip * pixels, slot0 + skip, total - skip));
-      check(rb_register(ctx_, slot0, total, offsets_, medians_));
+      check(rb_register(ctx_, slot0, total, offsets_, opt_.fetch_medians ? medians_ : nullptr));
 
       for (std::size_t i{0}; i < frames.size(); ++i) {
         auto& frame{frames[i]};
         auto& dim{frame.image_.dimensions()};
 
         image_type median{dim, alloc};
-        std::memcpy(median.data(), medians_ + (base + i) * pixels, pixels);
+        if (opt_.fetch_medians) {
+          std::memcpy(median.data(), medians_ + (base + i) * pixels, pixels);
+        }
 
         bool init{first_batch && i == 0};
         if (init) {
@@ -175,7 +184,8 @@ public:
 
         auto& [no, image]{frame};
         if (opt_.gpu_blit) { // same record as fragment::blit leaves (src/fgm.hpp:96), the dots come later
-          pending_.emplace_back(no, position_, fgm::packed_data{comp(image), comp(median)});
+          pending_.emplace_back(no, position_,
+                                opt_.keep_packed ? fgm::packed_data{comp(image), comp(median)} : fgm::packed_data{});
           slots_.push_back(static_cast<std::uint32_t>(count_));
           numbers_.push_back(no);
         }

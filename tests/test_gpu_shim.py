@@ -73,3 +73,11 @@ def test_filter_shim_resident_mode(tmp_path):
     seq = synth.scrolling_tilemap(90, 320, 224, seed=22, sprites=5, cut_every=40)
     out = _run(seq.frames, 32, False, str(tmp_path), gpu_blit=True, filter=True)
     assert "FILTER IDENTICAL" in out and "RESIDENT FILTER IDENTICAL" in out, out
+
+
+def test_lean_collector_and_resident_filter(tmp_path):
+    """gpu_blit = 2: the collector keeps no compressed copies and fetches no medians; its fragments (dots from
+    rb_blit_blend) still equal the reference's, and pass 2 runs on ITS fragments in resident mode."""
+    seq = synth.scrolling_tilemap(90, 320, 224, seed=23, sprites=5, cut_every=40)
+    out = _run(seq.frames, 32, False, str(tmp_path), gpu_blit=2, filter=True)
+    assert "RESIDENT FILTER IDENTICAL" in out and "\nIDENTICAL" in "\n" + out, out

@@ -17,10 +17,13 @@ def main():
     with tempfile.TemporaryDirectory() as td:
         p = os.path.join(td, "f.bin")
         seq.frames.tofile(p)
-        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "shim_harness"), p, "320", "224", "2000", "512", "0", "1", "1", "0"],
-                           capture_output=True, text=True)
-        print(r.stdout[-800:], r.stderr[-300:])
-        return r.returncode
+        rc = 0
+        for mode in ("1", "2"):  # 1: compatible collector (compressed copies kept); 2: lean (frames stay on the device)
+            r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "shim_harness"), p, "320", "224", "2000", "512", "0", mode, "1", "0"],
+                               capture_output=True, text=True)
+            print(f"gpu_blit={mode}:", r.stdout[-800:], r.stderr[-300:])
+            rc |= r.returncode
+        return rc
 
 
 if __name__ == "__main__":
