@@ -181,7 +181,9 @@ def next_rows():
             if r and (best is None or sum(t.values()) < sum(best.values())):
                 best = t
         tot = sum(best.values())
+        fg_bytes = 2 * W * H + H * ((W + 31) // 32) * 4  # frame + median read, bit map written
         out["filter_fragment"] = {"replaces": "fdf::filter (src/fdf.hpp:40-75)", "frames": int(len(idx)),
+                                  "foreground_GBps": fg_bytes * len(idx) / (best["foreground"] * 1e-3) / 1e9,
                                   "frames_per_s": len(idx) / (tot * 1e-3), "ms": {k: round(v, 3) for k, v in best.items()},
                                   "contours_per_frame": float(res["ncontours"].mean()), "frames_deferred": res["frames_deferred"]}
     rng = np.random.default_rng(7)
@@ -418,6 +420,14 @@ def main():
             "algorithmic_bytes_per_launch": dom_bytes,
             "kernel_ms": {k: v / args.steps for k, v in kt.items()},
             "kernel_share_of_step": {"kpe": kpe_s / step_s, "kpm": kpm_s / step_s},
+            # per stage: algorithmic bytes of the stage (SURVEY.md 8(d) split) / its CUDA-event time, against the same peak
+            "stages": {
+                "kpe (rb_kpe_kernel)": {"bytes_per_frame": b_kpe, "achieved": b_kpe * n / kpe_s / 1e9,
+                                        "frac": b_kpe * n / kpe_s / 1e9 / peak, "bound_by": "ALU pipe (LOP3), ncu r1h 84 %"},
+                "kpm (rb_list_kernel + rb_kpm_fast_kernel + K3)": {"bytes_per_frame": b_kpm, "achieved": b_kpm * n / kpm_s / 1e9,
+                                                                    "frac": b_kpm * n / kpm_s / 1e9 / peak,
+                                                                    "bound_by": "instruction issue + shared-memory latency, ncu r1h issue-active 61 %"},
+            },
             "path": {"bytes_per_frame": b_path, "achieved": b_path * n / step_s / 1e9,
                      "frac": b_path * n / step_s / 1e9 / peak},
             "deferred_ballots": deferred,
