@@ -62,15 +62,34 @@ __global__ void __launch_bounds__(RB_BLIT_NT) rb_blit_blend_kernel(const uint8_t
     }
     __syncthreads();
     const uint32_t nh = nhit;
-    for (uint32_t j = 0; j < nh; ++j) {
+    // One frame pixel (and, masked, one mask word) per hit: four hits' loads are issued before any histogram (eight: more registers, fewer CTAs, no gain)
+    // update -- the updates are shared-memory stores the compiler will not move loads across, and a single load
+    // in flight per thread left this loop latency-bound (1.3 pixels per cycle and SM).
+    auto pixel_of = [&](uint32_t j, bool& take) -> uint32_t {
       const RbPlacement p = hit[j];
       const uint32_t fx = mx - (uint32_t)p.x, fy = my - (uint32_t)p.y;  // unsigned: negative wraps far above W / H
-      bool take = fx < W && fy < H;
-      if (MASKED && take) take = !((__ldg(fgbits + ((uint64_t)hit_idx[j] * H + fy) * NW + (fx >> 5)) >> (fx & 31)) & 1u);
+      take = fx < W && fy < H;
+      uint32_t c = 0, m = 0;
       if (take) {
-        const uint32_t c = frames[(uint64_t)p.frame * frame_stride + (uint64_t)fy * pitch + fx] & 15u;
-        ++hist[c][tid];  // uint16: wraps at 65,536 like fgm::dot_type (src/fgm.hpp:14,94)
+        c = frames[(uint64_t)p.frame * frame_stride + (uint64_t)fy * pitch + fx];
+        if (MASKED) m = __ldg(fgbits + ((uint64_t)hit_idx[j] * H + fy) * NW + (fx >> 5)) >> (fx & 31);
       }
+      if (MASKED && (m & 1u)) take = false;
+      return c & 15u;
+    };
+    uint32_t j = 0;
+    for (; j + 4 <= nh; j += 4) {
+      bool t0, t1, t2, t3;
+      const uint32_t c0 = pixel_of(j, t0), c1 = pixel_of(j + 1, t1), c2 = pixel_of(j + 2, t2), c3 = pixel_of(j + 3, t3);
+      if (t0) ++hist[c0][tid];  // uint16: wraps at 65,536 like fgm::dot_type (src/fgm.hpp:14,94)
+      if (t1) ++hist[c1][tid];
+      if (t2) ++hist[c2][tid];
+      if (t3) ++hist[c3][tid];
+    }
+    for (; j < nh; ++j) {
+      bool t0;
+      const uint32_t c0 = pixel_of(j, t0);
+      if (t0) ++hist[c0][tid];
     }
     __syncthreads();
   }
