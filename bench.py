@@ -445,11 +445,11 @@ def main():
         achieved = dom_bytes / dom_s / 1e9
         step_s = max_ms * 1e-3 / args.steps
         # DRAM bytes of the dominant kernel per launch: dram__bytes_read + dram__bytes_write of the ncu --set full
-        # capture committed as profiles/r1h_ncu_full_summary.csv (4,000 frames of this workload), scaled to n frames
-        ncu_bytes_per_frame = {"rb_kpe_kernel": (349.32e6 + 342.84e6) / 4000.0,
-                               "rb_kpm_fast_kernel (+ rb_list_kernel)": (213.62e6 + 7.07e6 + 87.3e6 + 45.9e6) / 4000.0}
+        # capture committed as profiles/r1n_ncu_full_summary.csv (4,000 frames of this workload), scaled to n frames
+        ncu_bytes_per_frame = {"rb_kpe_kernel": (348.96e6 + 341.79e6) / 4000.0,
+                               "rb_kpm_fast_kernel (+ rb_list_kernel)": (213.17e6 + 6.05e6 + 87.23e6 + 48.11e6) / 4000.0}
         traffic = ncu_bytes_per_frame[dominant] * n if (args.width, args.height) == (320, 224) else None
-        traffic_src = "profiles/r1h_ncu_full_summary.csv (ncu --set full, 4,000 frames), scaled per frame" if traffic else None
+        traffic_src = "profiles/r1n_ncu_full_summary.csv (ncu --set full, 4,000 frames), scaled per frame" if traffic else None
         roofline = {
             "bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
