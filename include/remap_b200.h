@@ -169,6 +169,18 @@ int rb_blit_blend(rb_ctx* ctx, const rb_placement* placements, size_t n, uint32_
  * over the reduced dots on the destination rank.  Pointers stay valid until the context's next map call. */
 int rb_map_device(rb_ctx* ctx, uint16_t** dots, uint8_t** image, uint8_t** mask, uint32_t* mapW, uint32_t* mapH);
 int rb_blend_map(rb_ctx* ctx, uint16_t* out_dots, uint8_t* out_image, uint8_t* out_mask);
+/* The same as ONE kernel over peer memory: every rank exports its partial map (rb_map_export: a CUDA-IPC handle of
+ * the map scratch; ship the 80 bytes to the destination rank any way you like), the destination rank calls
+ * rb_blend_map_peers with the other ranks' handles: its kernel reads the peers' dot maps in place over NVLink,
+ * adds them to its own (uint16 lanes, wrapping) and blends in the same pass -- no staging buffers, no second pass.
+ * The peers must not touch their map scratch until the call has returned (a barrier on the caller's side). */
+typedef struct rb_map_handle {
+  uint8_t opaque[64];  /* cudaIpcMemHandle_t */
+  uint32_t map_w, map_h, device, reserved;
+} rb_map_handle;
+int rb_map_export(rb_ctx* ctx, rb_map_handle* out);
+int rb_blend_map_peers(rb_ctx* ctx, const rb_map_handle* peers, size_t npeers, uint16_t* out_dots, uint8_t* out_image,
+                       uint8_t* out_mask);
 
 /* Pass-2 foreground filtering of one fragment: fdf::filter (src/fdf.hpp:40-75).  For every
  * placed frame: fde::extractor::extract (src/fde.hpp:83-103: generate_mask against the background window, the

@@ -223,6 +223,27 @@ class Registrar:
                                            image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
         return dots, image, mask
 
+    def map_export(self) -> bytes:
+        """CUDA-IPC handle (rb_map_handle, 80 bytes) of this context's map scratch, for rb_blend_map_peers on
+        another rank."""
+        buf = (C.c_uint8 * 80)()
+        self._check(self._lib.rb_map_export(self._ctx, buf))
+        return bytes(buf)
+
+    def blend_map_peers(self, handles, want_dots=True):
+        """Sum this rank's partial dot map with the peers' (read in place over NVLink) and blend, in one kernel.
+        handles: list of bytes from the other ranks' map_export().  -> (dots | None, image, mask)"""
+        md = self.map_device()
+        h, w = md["height"], md["width"]
+        raw = b"".join(handles)
+        arr = (C.c_uint8 * max(len(raw), 1)).from_buffer_copy(raw or b"\0")
+        dots = np.zeros((h, w, 16), np.uint16) if want_dots else None
+        image = np.zeros((h, w), np.uint8)
+        mask = np.zeros((h, w), np.uint8)
+        self._check(self._lib.rb_blend_map_peers(self._ctx, arr, len(handles), dots.ctypes.data_as(C.c_void_p) if want_dots else None,
+                                                 image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
+        return dots, image, mask
+
     def aws_compare(self, n, first=0, heat=None):
         """aws::details::compare (src/aws.hpp:37-60) over every consecutive pair of resident frames
         [first, first + n).  heat: (H, W) uint8 to continue from, or None for aws::scan's initial map of ones

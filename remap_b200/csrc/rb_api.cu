@@ -10,6 +10,7 @@
 
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/remap_b200.h"
@@ -333,6 +334,7 @@ struct rb_ctx {
   uint8_t* d_map;         // dots (32 B / map pixel) + image + mask
   size_t map_cap;
   uint32_t map_w, map_h;  // geometry of the map the scratch holds (last rb_blit_blend / rb_filter_fragment)
+  std::vector<std::pair<std::string, void*>> ipc_open;  // peers' map scratch mapped through CUDA IPC (handle bytes -> address)
   uint8_t* d_bg;       // scratch for rb_foreground_mask
   size_t bg_cap;
   uint8_t* d_fgframe;  // dense frame scratch
@@ -617,6 +619,7 @@ void rb_destroy(rb_ctx* c) {
   cudaFree(c->d_frames); cudaFree(c->d_median); cudaFree(c->d_kp); cudaFree(c->d_w2); cudaFree(c->d_votes);
   cudaFree(c->d_results); cudaFree(c->d_offsets); cudaFree(c->d_tap_bins); cudaFree(c->d_tap_count);
   cudaFree(c->d_kps); cudaFree(c->d_places); cudaFree(c->d_map); cudaFree(c->d_bg); cudaFree(c->d_fgframe); cudaFree(c->d_mask);
+  for (auto& kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
   cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred); cudaFree(c->d_fg_count); cudaFree(c->d_fg_scratch);
   cudaFree(c->d_fg_bytes);
   for (int i = 0; i < 4; ++i)
@@ -1295,7 +1298,8 @@ int rb_filter_fragment(rb_ctx* c, const rb_placement* placements, size_t n, uint
   }
   const size_t fwords = (size_t)g.H * c->fg_NW;
   if (n > c->fg_cap) {
-    cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred);
+    for (auto& kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
+  cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred);
     c->bytes -= c->fg_cap * (fwords * 4 + 8);
     c->d_fgbits = c->d_fg_nkept = c->d_fg_deferred = nullptr;
     c->fg_cap = 0;
@@ -1658,6 +1662,60 @@ int rb_blend_map(rb_ctx* c, uint16_t* out_dots, uint8_t* out_image, uint8_t* out
   if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
   if (out_mask) RB_CUDA(c, cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+// Fused multi-GPU map assembly: export this rank's partial map, and (on the destination rank) sum + blend over
+// the peers' maps through CUDA IPC.
+int rb_map_export(rb_ctx* c, rb_map_handle* out) {
+  if (!c || !out) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_map_export: no map assembled yet"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  memset(out, 0, sizeof(*out));
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(out->opaque), "rb_map_handle too small");
+  cudaIpcMemHandle_t h;
+  RB_CUDA(c, cudaIpcGetMemHandle(&h, c->d_map));
+  memcpy(out->opaque, &h, sizeof(h));
+  out->map_w = c->map_w; out->map_h = c->map_h; out->device = (uint32_t)c->device;
+  return RB_OK;
+}
+
+int rb_blend_map_peers(rb_ctx* c, const rb_map_handle* peers, size_t npeers, uint16_t* out_dots, uint8_t* out_image,
+                       uint8_t* out_mask) {
+  if (!c || (!peers && npeers) || npeers > RB_MAX_PEERS) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_blend_map_peers: no map assembled yet"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RbPeerMaps pm;
+  memset(&pm, 0, sizeof(pm));
+  for (size_t i = 0; i < npeers; ++i) {
+    if (peers[i].map_w != c->map_w || peers[i].map_h != c->map_h) { c->err = "rb_blend_map_peers: map geometry differs"; return RB_ERR_INVALID; }
+    // a peer's scratch keeps its address (and handle) until it grows: mappings are opened once and kept
+    const std::string key(reinterpret_cast<const char*>(peers[i].opaque), sizeof(cudaIpcMemHandle_t));
+    void* addr = nullptr;
+    for (auto& kv : c->ipc_open)
+      if (kv.first == key) addr = kv.second;
+    if (!addr) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, peers[i].opaque, sizeof(h));
+      const cudaError_t e = cudaIpcOpenMemHandle(&addr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); return RB_ERR_CUDA; }
+      c->ipc_open.emplace_back(key, addr);
+    }
+    pm.dots[i] = static_cast<const uint16_t*>(addr);
+  }
+  pm.n = (uint32_t)npeers;
+  const size_t px = (size_t)c->map_w * c->map_h;
+  uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
+  uint8_t* d_img = c->d_map + px * 32;
+  uint8_t* d_msk = d_img + px;
+  rb_blend_peers_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_dots, pm, c->map_w, c->map_h, d_img, c->map_w, d_msk);
+  ++c->launches;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && out_dots) e = cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && out_image) e = cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess && out_mask) e = cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { c->err = std::string("rb_blend_map_peers: ") + cudaGetErrorString(e); return RB_ERR_CUDA; }
   return RB_OK;
 }
 

@@ -164,6 +164,40 @@ __global__ void rb_blend_kernel(const uint16_t* __restrict__ dots, uint32_t W, u
   }
 }
 
+// Multi-GPU map assembly as ONE kernel: rank 0 sums its own partial dot map and the peers' partial maps -- read
+// in place over NVLink through CUDA-IPC mappings of their map scratch -- and blends in the same pass
+// (fgm::fragment::blend, src/fgm.hpp:115-135).  The uint16 counters add per 16-bit lane and wrap like the
+// reference's (src/fgm.hpp:12-14,94).  32 B per map pixel and peer cross the link, once.
+#define RB_MAX_PEERS 15
+struct RbPeerMaps {
+  const uint16_t* dots[RB_MAX_PEERS];
+  uint32_t n;
+};
+__device__ __forceinline__ uint32_t rb_add16x2(uint32_t a, uint32_t b) {  // two independent uint16 sums, each mod 65,536
+  return ((a & 0x7FFF7FFFu) + (b & 0x7FFF7FFFu)) ^ ((a ^ b) & 0x80008000u);
+}
+__global__ void rb_blend_peers_kernel(uint16_t* __restrict__ dots, const RbPeerMaps peers, uint32_t W, uint32_t H,
+                                      uint8_t* __restrict__ image, uint32_t pitch, uint8_t* __restrict__ mask) {
+  const size_t total = (size_t)W * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    uint4* own = reinterpret_cast<uint4*>(dots + i * 16);
+    uint4 a = own[0], b = own[1];
+    for (uint32_t r = 0; r < peers.n; ++r) {
+      const uint4* q = reinterpret_cast<const uint4*>(peers.dots[r] + i * 16);
+      const uint4 pa = q[0], pb = q[1];  // peer memory: plain loads over NVLink
+      a.x = rb_add16x2(a.x, pa.x); a.y = rb_add16x2(a.y, pa.y); a.z = rb_add16x2(a.z, pa.z); a.w = rb_add16x2(a.w, pa.w);
+      b.x = rb_add16x2(b.x, pb.x); b.y = rb_add16x2(b.y, pb.y); b.z = rb_add16x2(b.z, pb.z); b.w = rb_add16x2(b.w, pb.w);
+    }
+    own[0] = a; own[1] = b;
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint16_t d[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { d[2 * k] = (uint16_t)(v[k] & 0xFFFFu); d[2 * k + 1] = (uint16_t)(v[k] >> 16); }
+    const uint32_t y = (uint32_t)(i / W), x = (uint32_t)(i - (size_t)y * W);
+    rbs::blend_pixel(d, image + (size_t)y * pitch + x, mask + i);
+  }
+}
+
 __global__ void rb_snip_emit_kernel(const RbGeom g, const uint8_t* __restrict__ image, const uint32_t* __restrict__ kpbits,
                                     const uint32_t* __restrict__ w2bits, RbSnipKp* out, uint32_t cap, uint32_t* count) {
   const uint32_t total = g.H * g.NS;

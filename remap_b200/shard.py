@@ -131,7 +131,7 @@ class _DeviceArray:
         self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def reduce_fragment_map(reg, group=None, dst: int = 0):
+def reduce_fragment_map(reg, group=None, dst: int = 0, want_dots: bool = True):
     """Multi-GPU map assembly.  Every rank has called ``reg.blit_blend`` (or
     ``reg.filter_fragment``) with ITS frames of one fragment and the fragment's full map geometry; this sums the
     partial dot maps to rank ``dst`` with one reduction (NCCL over NVLink on GPUs; through host memory when the
@@ -159,4 +159,32 @@ def reduce_fragment_map(reg, group=None, dst: int = 0):
     low = wide & 0xFFFF
     part16.copy_((((low + 0x8000) & 0xFFFF) - 0x8000).to(torch.int16))  # same bits as the uint16 value
     torch.cuda.current_stream().synchronize()
-    return reg.blend_map()
+    return reg.blend_map(want_dots=want_dots)
+
+
+def exchange_map_handles(reg, group=None):
+    """Every rank's map_export() on every rank.  A handle stays valid until that rank's map scratch grows, so one
+    exchange serves all fragments that fit the first one's scratch."""
+    import torch.distributed as dist
+
+    handles = [None] * dist.get_world_size(group)
+    dist.all_gather_object(handles, reg.map_export(), group=group)
+    return handles
+
+
+def reduce_fragment_map_fused(reg, group=None, dst: int = 0, want_dots: bool = True, handles=None):
+    """reduce_fragment_map as ONE kernel over peer memory: the ranks exchange 80-byte CUDA-IPC handles of their
+    partial dot maps (all_gather_object), rank ``dst`` reads the peers' maps in place over NVLink, sums and blends
+    in a single pass (rb_blend_map_peers); a barrier keeps the peers' maps alive until it is done.  Pass `handles`
+    from an earlier exchange_map_handles() to skip the exchange.
+    -> (dots, image, mask) on rank ``dst``, None elsewhere."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    if handles is None:
+        handles = exchange_map_handles(reg, group)
+    out = None
+    if rank == dst:
+        out = reg.blend_map_peers([h for r, h in enumerate(handles) if r != dst], want_dots=want_dots)
+    dist.barrier(group=group)
+    return out

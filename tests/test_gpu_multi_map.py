@@ -55,7 +55,12 @@ def _worker(rank, world, port, n_frames, backend, q):
             pl = np.zeros(len(own), PLACEMENT_DTYPE)
             pl["frame"], pl["x"], pl["y"] = own - first, pos[own, 1] - zx, pos[own, 2] - zy
             reg.blit_blend(pl, mw, mh, want_dots=False)
+            fused = shard.reduce_fragment_map_fused(reg)          # one kernel over the peers' maps (CUDA IPC)
+            reg.blit_blend(pl, mw, mh, want_dots=False)          # the partial map again: rank 0's now holds the sum
             plain = shard.reduce_fragment_map(reg)
+            if rank == 0:
+                for a, b in zip(fused, plain):
+                    assert np.array_equal(a, b), "fused peer-memory reduction differs from the NCCL / gloo one"
             bg = [plain[1] if rank == 0 else None]
             dist.broadcast_object_list(bg, src=0)                # the background of pass 2 is the blend of ALL frames
             reg.filter_fragment(pl, mw, mh, background=bg[0], want_dots=False)
