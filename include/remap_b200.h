@@ -181,6 +181,14 @@ typedef struct rb_map_handle {
 int rb_map_export(rb_ctx* ctx, rb_map_handle* out);
 int rb_blend_map_peers(rb_ctx* ctx, const rb_map_handle* peers, size_t npeers, uint16_t* out_dots, uint8_t* out_image,
                        uint8_t* out_mask);
+/* The all-links form for many GPUs (reduce-scatter, then gather).  ranks[r] = rank r's handle (ranks[self] is
+ * ignored), world <= 15.  Step 1, on EVERY rank: rb_sum_map_slice sums slice `self` of the map (pixels
+ * [self * ceil(px / world), ...)) over all other ranks into this rank's scratch -- every NVLink carries 1/world of a
+ * map per peer at the same time.  Barrier.  Step 2, on the destination rank: rb_blend_map_slices pulls each slice from
+ * the rank that reduced it and blends.  Barrier before anyone touches its scratch again. */
+int rb_sum_map_slice(rb_ctx* ctx, const rb_map_handle* ranks, size_t world, size_t self);
+int rb_blend_map_slices(rb_ctx* ctx, const rb_map_handle* ranks, size_t world, size_t self, uint16_t* out_dots,
+                        uint8_t* out_image, uint8_t* out_mask);
 
 /* Pass-2 foreground filtering of one fragment: fdf::filter (src/fdf.hpp:40-75).  For every
  * placed frame: fde::extractor::extract (src/fde.hpp:83-103: generate_mask against the background window, the

@@ -24,7 +24,7 @@ SYMBOLS = [
     "rb_kernel_launches", "rb_device_bytes", "rb_last_error", "rb_abi_version", "rb_offsets_device",
     "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count", "rb_register_host_async", "rb_blit_blend",
     "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
-    "rb_aws_compare", "rb_map_device", "rb_blend_map", "rb_map_export", "rb_blend_map_peers", "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
+    "rb_aws_compare", "rb_map_device", "rb_blend_map", "rb_map_export", "rb_blend_map_peers", "rb_sum_map_slice", "rb_blend_map_slices", "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
 ]
 
 
@@ -91,6 +91,10 @@ def load(build_if_missing: bool = False):
     lib.rb_map_export.argtypes = [vp, vp]
     lib.rb_blend_map_peers.restype = C.c_int
     lib.rb_blend_map_peers.argtypes = [vp, vp, sz, vp, vp, vp]
+    lib.rb_sum_map_slice.restype = C.c_int
+    lib.rb_sum_map_slice.argtypes = [vp, vp, sz, sz]
+    lib.rb_blend_map_slices.restype = C.c_int
+    lib.rb_blend_map_slices.argtypes = [vp, vp, sz, sz, vp, vp, vp]
     lib.rb_blend_map.restype = C.c_int
     lib.rb_blend_map.argtypes = [vp, vp, vp, vp]
     lib.rb_aws_compare.restype = C.c_int

@@ -244,6 +244,26 @@ class Registrar:
                                                  image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
         return dots, image, mask
 
+    def sum_map_slice(self, handles, self_index):
+        """Reduce-scatter step of the all-links map reduction: sum slice `self_index` over all other ranks' maps."""
+        raw = b"".join(handles)
+        arr = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        self._check(self._lib.rb_sum_map_slice(self._ctx, arr, len(handles), self_index))
+
+    def blend_map_slices(self, handles, self_index, want_dots=True):
+        """Gather step on the destination rank: pull every reduced slice from its rank and blend."""
+        md = self.map_device()
+        h, w = md["height"], md["width"]
+        raw = b"".join(handles)
+        arr = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        dots = np.zeros((h, w, 16), np.uint16) if want_dots else None
+        image = np.zeros((h, w), np.uint8)
+        mask = np.zeros((h, w), np.uint8)
+        self._check(self._lib.rb_blend_map_slices(self._ctx, arr, len(handles), self_index,
+                                                  dots.ctypes.data_as(C.c_void_p) if want_dots else None,
+                                                  image.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p)))
+        return dots, image, mask
+
     def aws_compare(self, n, first=0, heat=None):
         """aws::details::compare (src/aws.hpp:37-60) over every consecutive pair of resident frames
         [first, first + n).  heat: (H, W) uint8 to continue from, or None for aws::scan's initial map of ones

@@ -1680,6 +1680,72 @@ int rb_map_export(rb_ctx* c, rb_map_handle* out) {
   return RB_OK;
 }
 
+// a peer's scratch keeps its address (and handle) until it grows: mappings are opened once and kept
+static int peer_address(rb_ctx* c, const rb_map_handle& h, const uint16_t** out) {
+  if (h.map_w != c->map_w || h.map_h != c->map_h) { c->err = "peer map geometry differs"; return RB_ERR_INVALID; }
+  const std::string key(reinterpret_cast<const char*>(h.opaque), sizeof(cudaIpcMemHandle_t));
+  for (auto& kv : c->ipc_open)
+    if (kv.first == key) { *out = static_cast<const uint16_t*>(kv.second); return RB_OK; }
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, h.opaque, sizeof(ih));
+  void* addr = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&addr, ih, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); return RB_ERR_CUDA; }
+  c->ipc_open.emplace_back(key, addr);
+  *out = static_cast<const uint16_t*>(addr);
+  return RB_OK;
+}
+
+// reduce-scatter step: this rank sums slice `self` of `world` over all other ranks' maps into its own scratch
+int rb_sum_map_slice(rb_ctx* c, const rb_map_handle* ranks, size_t world, size_t self) {
+  if (!c || !ranks || world < 1 || world > RB_MAX_PEERS || self >= world) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_sum_map_slice: no map assembled yet"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RbPeerMaps pm;
+  memset(&pm, 0, sizeof(pm));
+  for (size_t r = 0; r < world; ++r) {
+    if (r == self) continue;
+    const int rc = peer_address(c, ranks[r], &pm.dots[pm.n]);
+    if (rc != RB_OK) return rc;
+    ++pm.n;
+  }
+  const size_t px = (size_t)c->map_w * c->map_h, len = (px + world - 1) / world;
+  const size_t i0 = self * len < px ? self * len : px, i1 = (self + 1) * len < px ? (self + 1) * len : px;
+  if (i1 > i0) {
+    rb_sum_slice_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(reinterpret_cast<uint16_t*>(c->d_map), pm, i0, i1);
+    RB_LAUNCHED(c, "rb_sum_slice_kernel");
+  }
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+// gather step on the destination rank: pull every slice from the rank that reduced it, blend
+int rb_blend_map_slices(rb_ctx* c, const rb_map_handle* ranks, size_t world, size_t self, uint16_t* out_dots, uint8_t* out_image,
+                        uint8_t* out_mask) {
+  if (!c || !ranks || world < 1 || world > RB_MAX_PEERS || self >= world) return RB_ERR_INVALID;
+  if (!c->d_map || c->map_w == 0) { c->err = "rb_blend_map_slices: no map assembled yet"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  RbPeerMaps pm;
+  memset(&pm, 0, sizeof(pm));
+  pm.n = (uint32_t)world;
+  for (size_t r = 0; r < world; ++r) {
+    if (r == self) continue;
+    const int rc = peer_address(c, ranks[r], &pm.dots[r]);
+    if (rc != RB_OK) return rc;
+  }
+  const size_t px = (size_t)c->map_w * c->map_h, len = (px + world - 1) / world;
+  uint16_t* d_dots = reinterpret_cast<uint16_t*>(c->d_map);
+  uint8_t* d_img = c->d_map + px * 32;
+  uint8_t* d_msk = d_img + px;
+  rb_gather_blend_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_dots, pm, len, c->map_w, c->map_h, d_img, c->map_w, d_msk);
+  RB_LAUNCHED(c, "rb_gather_blend_kernel");
+  if (out_dots) RB_CUDA(c, cudaMemcpyAsync(out_dots, d_dots, px * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (out_image) RB_CUDA(c, cudaMemcpyAsync(out_image, d_img, px, cudaMemcpyDeviceToHost, c->stream));
+  if (out_mask) RB_CUDA(c, cudaMemcpyAsync(out_mask, d_msk, px, cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
 int rb_blend_map_peers(rb_ctx* c, const rb_map_handle* peers, size_t npeers, uint16_t* out_dots, uint8_t* out_image,
                        uint8_t* out_mask) {
   if (!c || (!peers && npeers) || npeers > RB_MAX_PEERS) return RB_ERR_INVALID;
@@ -1688,20 +1754,8 @@ int rb_blend_map_peers(rb_ctx* c, const rb_map_handle* peers, size_t npeers, uin
   RbPeerMaps pm;
   memset(&pm, 0, sizeof(pm));
   for (size_t i = 0; i < npeers; ++i) {
-    if (peers[i].map_w != c->map_w || peers[i].map_h != c->map_h) { c->err = "rb_blend_map_peers: map geometry differs"; return RB_ERR_INVALID; }
-    // a peer's scratch keeps its address (and handle) until it grows: mappings are opened once and kept
-    const std::string key(reinterpret_cast<const char*>(peers[i].opaque), sizeof(cudaIpcMemHandle_t));
-    void* addr = nullptr;
-    for (auto& kv : c->ipc_open)
-      if (kv.first == key) addr = kv.second;
-    if (!addr) {
-      cudaIpcMemHandle_t h;
-      memcpy(&h, peers[i].opaque, sizeof(h));
-      const cudaError_t e = cudaIpcOpenMemHandle(&addr, h, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) { c->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); cudaGetLastError(); return RB_ERR_CUDA; }
-      c->ipc_open.emplace_back(key, addr);
-    }
-    pm.dots[i] = static_cast<const uint16_t*>(addr);
+    const int rc = peer_address(c, peers[i], &pm.dots[i]);
+    if (rc != RB_OK) return rc;
   }
   pm.n = (uint32_t)npeers;
   const size_t px = (size_t)c->map_w * c->map_h;

@@ -198,6 +198,47 @@ __global__ void rb_blend_peers_kernel(uint16_t* __restrict__ dots, const RbPeerM
   }
 }
 
+// The same reduction spread over all links (reduce-scatter, then gather): every rank sums ONE slice of the map --
+// pixels [i0, i1) -- over all peers into its own scratch (rb_sum_slice_kernel, all NVLinks busy at once), then the
+// destination rank pulls each slice from the rank that reduced it and blends (rb_gather_blend_kernel).  With the
+// single-destination kernel above, 7 x 275 MB enter one GPU; here 7/8 of one map does, twice.
+__global__ void rb_sum_slice_kernel(uint16_t* __restrict__ dots, const RbPeerMaps peers, size_t i0, size_t i1) {
+  for (size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (size_t)gridDim.x * blockDim.x) {
+    uint4* own = reinterpret_cast<uint4*>(dots + i * 16);
+    uint4 a = own[0], b = own[1];
+    for (uint32_t r = 0; r < peers.n; ++r) {
+      const uint4* q = reinterpret_cast<const uint4*>(peers.dots[r] + i * 16);
+      const uint4 pa = q[0], pb = q[1];
+      a.x = rb_add16x2(a.x, pa.x); a.y = rb_add16x2(a.y, pa.y); a.z = rb_add16x2(a.z, pa.z); a.w = rb_add16x2(a.w, pa.w);
+      b.x = rb_add16x2(b.x, pb.x); b.y = rb_add16x2(b.y, pb.y); b.z = rb_add16x2(b.z, pb.z); b.w = rb_add16x2(b.w, pb.w);
+    }
+    own[0] = a; own[1] = b;
+  }
+}
+// owners.dots[k] = scratch of the rank that reduced slice k (nullptr: this rank); slice k = pixels [k * len, (k + 1) * len)
+__global__ void rb_gather_blend_kernel(uint16_t* __restrict__ dots, const RbPeerMaps owners, size_t slice_len, uint32_t W,
+                                       uint32_t H, uint8_t* __restrict__ image, uint32_t pitch, uint8_t* __restrict__ mask) {
+  const size_t total = (size_t)W * H;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint16_t* src = owners.dots[i / slice_len];
+    uint4* own = reinterpret_cast<uint4*>(dots + i * 16);
+    uint4 a, b;
+    if (src) {
+      a = reinterpret_cast<const uint4*>(src + i * 16)[0];
+      b = reinterpret_cast<const uint4*>(src + i * 16)[1];
+      own[0] = a; own[1] = b;
+    } else {
+      a = own[0]; b = own[1];
+    }
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint16_t d[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { d[2 * k] = (uint16_t)(v[k] & 0xFFFFu); d[2 * k + 1] = (uint16_t)(v[k] >> 16); }
+    const uint32_t y = (uint32_t)(i / W), x = (uint32_t)(i - (size_t)y * W);
+    rbs::blend_pixel(d, image + (size_t)y * pitch + x, mask + i);
+  }
+}
+
 __global__ void rb_snip_emit_kernel(const RbGeom g, const uint8_t* __restrict__ image, const uint32_t* __restrict__ kpbits,
                                     const uint32_t* __restrict__ w2bits, RbSnipKp* out, uint32_t cap, uint32_t* count) {
   const uint32_t total = g.H * g.NS;

@@ -175,16 +175,24 @@ def exchange_map_handles(reg, group=None):
 def reduce_fragment_map_fused(reg, group=None, dst: int = 0, want_dots: bool = True, handles=None):
     """reduce_fragment_map as ONE kernel over peer memory: the ranks exchange 80-byte CUDA-IPC handles of their
     partial dot maps (all_gather_object), rank ``dst`` reads the peers' maps in place over NVLink, sums and blends
-    in a single pass (rb_blend_map_peers); a barrier keeps the peers' maps alive until it is done.  Pass `handles`
-    from an earlier exchange_map_handles() to skip the exchange.
+    in a single pass (rb_blend_map_peers); a barrier keeps the peers' maps alive until it is done.  With more than two
+    ranks the sum is spread over all links first: every rank reduces one slice of the map over its peers
+    (rb_sum_map_slice), then the destination pulls the reduced slices and blends (rb_blend_map_slices).  Pass
+    `handles` from an earlier exchange_map_handles() to skip the exchange.
     -> (dots, image, mask) on rank ``dst``, None elsewhere."""
     import torch.distributed as dist
 
-    rank = dist.get_rank(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     if handles is None:
         handles = exchange_map_handles(reg, group)
     out = None
-    if rank == dst:
-        out = reg.blend_map_peers([h for r, h in enumerate(handles) if r != dst], want_dots=want_dots)
+    if world <= 2:  # one kernel on the destination rank: the only peer's map crosses the link once
+        if rank == dst:
+            out = reg.blend_map_peers([h for r, h in enumerate(handles) if r != dst], want_dots=want_dots)
+    else:           # all links at once: every rank reduces one slice, the destination gathers the slices and blends
+        reg.sum_map_slice(handles, rank)
+        dist.barrier(group=group)
+        if rank == dst:
+            out = reg.blend_map_slices(handles, rank, want_dots=want_dots)
     dist.barrier(group=group)
     return out

@@ -72,15 +72,17 @@ def _worker(rank, world, port, n_frames, backend, q):
         dist.destroy_process_group()
 
 
-def test_two_rank_map_assembly_equals_single_process():
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_map_assembly_equals_single_process(world):
+    """world 2: the single-destination peer kernel; world 3: reduce-scatter over all links, then gather."""
     from oracle import oracle
     from remap_b200 import synth
     n_frames = 41
-    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    backend = "nccl" if torch.cuda.device_count() >= world else "gloo"
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_frames, backend, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_frames, backend, q)) for r in range(world)]
     for p in procs:
         p.start()
     pos, (zx, zy, mw, mh), plain, filt = q.get(timeout=600)
