@@ -143,3 +143,20 @@ def test_filter_needs_registered_frames():
         reg.register(3)
         with pytest.raises(remap_b200.RemapError):
             reg.filter_fragment(places_of([0], np.array([[1, 0]])), 96, 64)   # outside the map
+
+
+def test_filter_edge_cases():
+    """No placements (an empty fragment): all-zero dots, nothing masked.  One frame whose whole interior differs from
+    the background: every contour seeded; the big ones dropped by the area rule."""
+    frames = synth.random_frames(2, 96, 64, seed=38, palette=3)
+    with remap_b200.Registrar(96, 64, max_frames=2) as reg:
+        reg.upload(frames)
+        _, med = reg.register(2, want_medians=True)
+        out = reg.filter_fragment(np.zeros(0, PLACEMENT_DTYPE), 120, 80, want_fgmasks=True)
+        assert out["dots"].sum() == 0 and out["image"].sum() == 0 and out["mask"].sum() == 0 and len(out["ncontours"]) == 0
+        bg = np.full((80, 120), 15, np.uint8)       # a colour the 3-colour frames never use: every pixel a seed
+        pl = places_of([1], np.array([[7, 9]]))
+        out = reg.filter_fragment(pl, 120, 80, background=bg, want_fgmasks=True)
+        want = oracle.filter_fragment(frames[1:2], med[1:2], np.array([[7, 9]]), 120, 80, background=bg)
+        assert np.array_equal(out["fgmasks"], want["masks"]) and np.array_equal(out["dots"], want["dots"])
+        assert np.array_equal(out["ncontours"], want["ncontours"])

@@ -388,3 +388,13 @@ def test_aws_compare_matches_reference_and_oracle(golden_dir):
         heat, fc = reg.aws_compare(300)
     oh, ofc = oracle.aws_compare(screen)
     assert np.array_equal(heat, oh) and np.array_equal(fc, ofc)
+
+
+def test_aws_compare_single_frame_and_identical_frames():
+    frames = synth.random_frames(1, 96, 64, seed=9).repeat(5, axis=0)
+    with remap_b200.Registrar(96, 64, max_frames=5) as reg:
+        reg.upload(frames)
+        heat, fc = reg.aws_compare(1)               # no pair at all
+        assert heat.min() == 1 and (fc == 0xFFFFFFFF).all()
+        heat, fc = reg.aws_compare(5)               # five identical frames: nothing ever changes
+        assert heat.min() == 1 and (fc == 0xFFFFFFFF).all()
