@@ -476,8 +476,12 @@ def main():
             sample = min(n, max(args.cpu_sample, 64 * threads))
             r = cpu_reference(seq.frames[:sample], threads)
             r1 = cpu_reference(seq.frames[: max(sample // threads, 200)], 1)
+            frc_loop = None
+            if r["kind"] == "reference":  # the reference's whole per-frame loop: + nic compression x2 + fragment blit
+                from oracle import refdump
+                frc_loop = refdump.ref_bench(seq.frames[:sample], mode="frc", threads=threads)["fps_best"]
             cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
-                   "single_thread_value": r1["value"],
+                   "single_thread_value": r1["value"], "frc_collector_loop_value": frc_loop,
                    "sample": f"first {sample} frames of rank 0's sequence, one contiguous shard per host thread, "
                              "kpe::extractor::extract + kpm::match per frame (the reference runs its loop on one thread)"}
         line = {
