@@ -1395,6 +1395,8 @@ struct rb_snippet {
   RbSnipKp* d_kps;
   uint32_t nkp;
   unsigned long long* d_count;
+  uint8_t* d_scratch;   // rb_snippet_match work area of this snippet as `prev` (grown on demand, kept)
+  size_t scratch_cap;
   std::string err;
 };
 
@@ -1412,6 +1414,7 @@ void rb_snippet_destroy(rb_snippet* s) {
   cudaSetDevice(s->device);
   if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
   cudaFree(s->d_image); cudaFree(s->d_mask); cudaFree(s->d_kp); cudaFree(s->d_w2); cudaFree(s->d_kps); cudaFree(s->d_count);
+  cudaFree(s->d_scratch);
   delete s;
 }
 
@@ -1547,10 +1550,15 @@ int rb_snippet_match(rb_snippet* a, rb_snippet* b, uint32_t cell_w, uint32_t cel
   const size_t cellwords = ((size_t)p.CW * CH + 31) / 32;
   p.AW = p.cW / cell_w + 1;
   const size_t actwords = ((size_t)p.AW * (p.cH / cell_h + 1) + 31) / 32;
-  uint8_t* mem = nullptr;
   const size_t bytes = ((size_t)p.nbuckets + p.np + nbins + cellwords + actwords) * 4 + 64;
-  RS_CUDA(a, cudaMalloc(&mem, bytes));
-  struct Free { uint8_t* m; ~Free() { cudaFree(m); } } guard{mem};
+  if (bytes > a->scratch_cap) {  // cudaMalloc / cudaFree per match cost more than the match itself
+    cudaFree(a->d_scratch);
+    a->d_scratch = nullptr;
+    a->scratch_cap = 0;
+    RS_CUDA(a, cudaMalloc(&a->d_scratch, bytes));
+    a->scratch_cap = bytes;
+  }
+  uint8_t* mem = a->d_scratch;
   unsigned long long* d_out = reinterpret_cast<unsigned long long*>(mem);
   p.head = reinterpret_cast<uint32_t*>(mem + 64);
   p.next = p.head + p.nbuckets;
