@@ -135,6 +135,18 @@ RB_HD uint32_t rb_bool4(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3) {
   return rb_lop3<0xCA>(x3, g1, g0);  // x3 ? g1 : g0
 }
 
+// ---- warp-lockstep loops -------------------------------------------------------------------------
+// A data-dependent per-lane loop (one trip per set bit of the lane's word, say) lets the lanes of a warp drift
+// apart, and they do not reconverge by themselves: every sub-group then issues its own copy of the loop body
+// (measured: 2 to 8 active lanes per issued instruction).  while (RB_WARP_ANY(cond)) { if (cond) { ... } } makes
+// all lanes take the same number of trips: a warp vote on the device (all 32 lanes must reach it), plain `cond`
+// in the host build.
+#if defined(__CUDA_ARCH__)
+#define RB_WARP_ANY(c) (__any_sync(0xFFFFFFFFu, (c)) != 0)
+#else
+#define RB_WARP_ANY(c) (c)
+#endif
+
 // ---- block-level execution helpers ------------------------------------------------------------
 // Block kernels are written as a sequence of PHASES separated by barriers.  Code inside
 // RB_FOR_THREADS runs once per thread; code outside it must be block-uniform (it only reads shared

@@ -229,13 +229,8 @@ RB_HD void build_word(const RbFgParams& p, const RbFgWork<L>& s, const RbPlaceme
 // Every phase below is "for each word, for each set bit / run segment of the word".  The counts differ
 // from word to word, and a plain per-thread loop lets the lanes of a warp drift apart for good (measured:
 // 2 to 5 active lanes per issued instruction).  The loops are therefore written so that all lanes of a
-// warp take the same number of trips: RB_WARP_ANY(c) is a warp vote on the device (all 32 lanes must
-// reach it) and plain `c` in the host build.
-#if defined(__CUDA_ARCH__)
-#define RB_WARP_ANY(c) (__any_sync(0xFFFFFFFFu, (c)) != 0)
-#else
-#define RB_WARP_ANY(c) (c)
-#endif
+// warp take the same number of trips: RB_WARP_ANY(c) (rb_common.cuh) is a warp vote on the device (all 32 lanes
+// must reach it) and plain `c` in the host build.
 
 // find with path halving: any ancestor is a valid parent, so the plain store races harmlessly with other
 // finds; a CAS can only succeed on a root, and a root is never written here.

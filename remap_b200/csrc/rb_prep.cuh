@@ -78,6 +78,7 @@ RB_HD void lane_emit(const RbListLane& L, uint32_t ra, uint32_t kw, uint32_t ww,
   uint32_t at1 = cap - 1 - n1_before;  // wraps far above cap when the row is full
   const uint32_t yv = ((L.Y0 + ra + L.row0) << 16) + RB_STRIP_OUT * L.j;
   uint32_t w2 = ww, w1 = kw & ~ww;  // two short loops beat one loop that selects per bit
+  // (and beat one warp-lockstep loop that takes a weight-2 and a weight-1 bit per trip: 0.65 vs 0.72 ms, r1o)
   while (w2) {
     const uint32_t b = rb_ffs0(w2);
     w2 &= w2 - 1;
