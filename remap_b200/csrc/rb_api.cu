@@ -276,7 +276,7 @@ __global__ void rb_count_kernel(const uint32_t* __restrict__ bits, size_t nwords
 }
 
 // The general matcher (rb_kpm.cuh) over the (pair, region) list the pipelined matcher deferred.
-__global__ void __launch_bounds__(256) rb_kpm_deferred_kernel(const RbKpmParams p, const uint2* __restrict__ list,
+__global__ void __launch_bounds__(1024) rb_kpm_deferred_kernel(const RbKpmParams p, const uint2* __restrict__ list,
                                                               const uint32_t* __restrict__ count, uint32_t cap,
                                                               uint32_t* __restrict__ total) {
   extern __shared__ __align__(16) uint32_t rb_kpm_smem[];
@@ -357,6 +357,7 @@ struct rb_ctx {
   size_t bytes;
   uint32_t code_slots, off_slots, tile_pitch, tile_rows;
   size_t kpm_smem;
+  uint32_t kpm_nt;       // threads per CTA of the general matcher: 256, or more when shared memory allows few CTAs per SM
   size_t uploaded;       // frames [0, uploaded) hold data
   size_t reg_first, reg_n;
   RbBatchEvents bev[RB_MAX_BATCHES];  // profile marks per batch of the last call
@@ -500,6 +501,22 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     if (!cfg->code_slots && c->code_slots / 2 >= 2 * maxcols && c->code_slots > 1024) { c->code_slots /= 2; continue; }
     c->err = "region tiles + hash tables exceed the shared memory of one CTA";
     return RB_ERR_INVALID;
+  }
+  // Large regions (640x480: 125 KB of tiles and tables) leave room for one CTA per SM; with 256 threads that is 8
+  // warps per SM and the kernel crawls.  The body is written for any block size: give such a CTA the whole SM.
+  c->kpm_nt = 256;
+  {
+    int smem_sm = 0;
+    RB_CUDA(c, cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c->device));
+    const size_t per_sm = (size_t)smem_sm / (c->kpm_smem + 1024);
+    const uint32_t nt = per_sm <= 1 ? 1024u : per_sm == 2 ? 512u : 256u;
+    if (nt != 256) {
+      RbKpmParams q;
+      memset(&q, 0, sizeof(q));
+      q.code_slots = c->code_slots; q.off_slots = c->off_slots; q.tile_pitch = c->tile_pitch; q.tile_rows = c->tile_rows;
+      const size_t need = rbm::smem_words(q, nt) * sizeof(uint32_t);
+      if (need <= (size_t)smem_max) { c->kpm_nt = nt; c->kpm_smem = need; }
+    }
   }
   RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kpm_smem));
   RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->kpm_smem));
@@ -854,11 +871,11 @@ static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cu
       }
       uint32_t dgrid = (uint32_t)c->sm_count * 2;
       if (dgrid > f.deferred_cap) dgrid = f.deferred_cap;
-      rb_kpm_deferred_kernel<<<dgrid, 256, c->kpm_smem, c->stream>>>(p, glist, gcount, f.deferred_cap, c->d_work + 1);
+      rb_kpm_deferred_kernel<<<dgrid, c->kpm_nt, c->kpm_smem, c->stream>>>(p, glist, gcount, f.deferred_cap, c->d_work + 1);
       RB_LAUNCHED(c, "rb_kpm_deferred_kernel");
     } else {
       if (ev) { RB_CUDA(c, cudaEventRecord(ev[3], c->stream)); RB_CUDA(c, cudaEventRecord(ev[4], c->stream)); }
-      rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), 256, c->kpm_smem, c->stream>>>(p);
+      rb_kpm_kernel<<<(uint32_t)((n - 1) * g.nreg), c->kpm_nt, c->kpm_smem, c->stream>>>(p);
       RB_LAUNCHED(c, "rb_kpm_kernel");
     }
     if (ev) RB_CUDA(c, cudaEventRecord(ev[5], c->stream));
@@ -1100,7 +1117,7 @@ int rb_region_votes(rb_ctx* c, size_t pair, uint32_t region, rb_bin* out, size_t
   p.tap_bins = c->d_tap_bins; p.tap_cap = 1u << 20; p.tap_count = c->d_tap_count;
   p.tap_pair = 0; p.tap_region = region;
   // launch all regions of the pair (blockIdx -> region), only `region` dumps
-  rb_kpm_kernel<<<g.nreg, 256, c->kpm_smem, c->stream>>>(p);
+  rb_kpm_kernel<<<g.nreg, c->kpm_nt, c->kpm_smem, c->stream>>>(p);
   RB_LAUNCHED(c, "rb_kpm_kernel");
   uint32_t n = 0;
   RB_CUDA(c, cudaMemcpyAsync(&n, c->d_tap_count, 4, cudaMemcpyDeviceToHost, c->stream));

@@ -577,7 +577,7 @@ RB_HD void declare_pair(const RbGeom& g, const RbRegionVote* votes, RbPairResult
 }  // namespace rbm
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(256) rb_kpm_kernel(const RbKpmParams p) {
+__global__ void __launch_bounds__(1024) rb_kpm_kernel(const RbKpmParams p) {
   extern __shared__ __align__(16) uint32_t rb_kpm_smem[];
   const uint32_t pair = blockIdx.x / p.g.nreg, region = blockIdx.x % p.g.nreg;
   rbm::kpm_block(p, pair, region, rb_kpm_smem, blockDim.x);
