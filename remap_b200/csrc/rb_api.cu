@@ -340,7 +340,7 @@ struct rb_ctx {
   uint8_t* d_fgframe;  // dense frame scratch
   // pass-2 filter (rb_filter_fragment)
   bool fg_ready, fg_fast_ok;
-  uint32_t fg_NW, fg_rcap, fg_scap, fg_grid, fg_gen_rcap, fg_gen_grid;
+  uint32_t fg_NW, fg_rcap, fg_scap, fg_grid, fg_gen_rcap, fg_gen_grid, fg_gen_nt;
   size_t fg_smem, fg_gen_smem, fg_slab;
   uint32_t* d_fgbits;      // [placement][H][NW]
   uint32_t* d_fg_nkept;    // [placement]
@@ -1266,6 +1266,7 @@ static int fg_setup(rb_ctx* c) {
   RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_fg_general_kernel, RB_FG_NT, c->fg_gen_smem));
   if (occ < 1) occ = 1;
   if (occ > 2) occ = 2;
+  c->fg_gen_nt = occ == 1 ? 2 * RB_FG_NT : RB_FG_NT;  // a CTA that has the SM to itself gets twice the threads
   c->fg_gen_grid = (uint32_t)(occ * c->sm_count);
   c->fg_slab = (rbg::table_bytes<uint32_t>(rmax, rmax) + 255) & ~(size_t)255;
   RB_CUDA(c, dmalloc(c, &c->d_fg_scratch, c->fg_slab * c->fg_gen_grid));
@@ -1362,7 +1363,7 @@ int rb_filter_fragment(rb_ctx* c, const rb_placement* placements, size_t n, uint
     p.rcap = c->fg_gen_rcap; p.scap = c->fg_gen_rcap;
     p.scratch = c->d_fg_scratch; p.scratch_stride = c->fg_slab;
     const uint32_t blocks = n < c->fg_gen_grid ? (uint32_t)n : c->fg_gen_grid;
-    rb_fg_general_kernel<<<blocks, RB_FG_NT, c->fg_gen_smem, c->stream>>>(p);
+    rb_fg_general_kernel<<<blocks, c->fg_gen_nt, c->fg_gen_smem, c->stream>>>(p);
     RB_LAUNCHED(c, "rb_fg_general_kernel");
   }
   RB_CUDA(c, cudaEventRecord(c->fg_ev[2], c->stream));

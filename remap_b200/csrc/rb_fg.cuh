@@ -626,15 +626,16 @@ __global__ void __launch_bounds__(RB_FG_NT) rb_fg_kernel(const RbFgParams p) {
   }
 }
 
-// General variant: bit maps in shared memory, labels (32 bit) and statistics in this CTA's global slab.
-__global__ void __launch_bounds__(RB_FG_NT) rb_fg_general_kernel(const RbFgParams p) {
+// General variant: bit maps in shared memory, labels (32 bit) and statistics in this CTA's global slab.  Launched
+// with RB_FG_NT threads, or with twice as many when the bit maps leave room for only one CTA per SM (640x480).
+__global__ void __launch_bounds__(2 * RB_FG_NT) rb_fg_general_kernel(const RbFgParams p) {
   extern __shared__ __align__(16) uint8_t rb_fg_smem[];
   const RbFgWork<uint32_t> s =
       rbg::carve<uint32_t>(rb_fg_smem, p.scratch + p.scratch_stride * blockIdx.x, p.g.H, p.NW, p.rcap, p.scap);
   const uint32_t n = p.todo ? *p.ntodo : p.n;
   for (uint32_t j = blockIdx.x; j < n; j += gridDim.x) {
     const uint32_t i = p.todo ? p.todo[j] : j;
-    if (!rbg::frame_body(p, s, i, RB_FG_NT)) {  // cannot happen: the slab holds the worst case
+    if (!rbg::frame_body(p, s, i, blockDim.x)) {  // cannot happen: the slab holds the worst case
       if (threadIdx.x == 0) p.nkept[i] = 0xFFFFFFFFu;
       __syncthreads();
     }
