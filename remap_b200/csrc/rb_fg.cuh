@@ -614,12 +614,12 @@ RB_HD bool frame_body(const RbFgParams& p, const RbFgWork<L>& s, uint32_t i, uin
 #if defined(__CUDACC__)
 
 // Fast variant: everything in shared memory, 16-bit labels.  Frame i -> CTA i mod gridDim.
-__global__ void __launch_bounds__(RB_FG_NT) rb_fg_kernel(const RbFgParams p) {
+__global__ void __launch_bounds__(2 * RB_FG_NT) rb_fg_kernel(const RbFgParams p) {
   extern __shared__ __align__(16) uint8_t rb_fg_smem[];
   const size_t fixed = (rbg::fixed_bytes(p.g.H, p.NW) + 15) & ~(size_t)15;
   const RbFgWork<uint16_t> s = rbg::carve<uint16_t>(rb_fg_smem, rb_fg_smem + fixed, p.g.H, p.NW, p.rcap, p.scap);
   for (uint32_t i = blockIdx.x; i < p.n; i += gridDim.x) {
-    if (!rbg::frame_body(p, s, i, RB_FG_NT)) {
+    if (!rbg::frame_body(p, s, i, blockDim.x)) {
       if (threadIdx.x == 0) p.deferred[atomicAdd(p.ndeferred, 1u)] = i;
       __syncthreads();
     }
