@@ -197,7 +197,7 @@ public:
         if (!init) { // the reference does not call back for the first frame (src/frc.hpp:83-95)
           grid_type keys{allocator_t<char>{alloc}};
           if (opt_.fill_keys) {
-            fill(keys, base + i);
+            fill(keys, slot0 + base + i);  // the frame's slot in the device store (== base + i unless gpu_blit)
           }
           cb(*current_, frame, median, keys);
         }

@@ -367,6 +367,7 @@ struct rb_ctx {
   cudaStream_t copy_stream;  // host -> device copies of rb_register_host_async
   cudaEvent_t ev_copy[2], ev_entry;
   uint8_t* h_stage[2];     // pinned staging: two chunks of packed 4 bit/pixel frames
+  uint32_t* h_flags;       // pinned: copy of d_work[0..3] fetched with the offsets ([2] = matcher error word)
   size_t stage_frames;
   uint64_t launches;
   bool debug_sync;
@@ -469,6 +470,8 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   RB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
   RB_CUDA(c, cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+  RB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_flags), 64, cudaHostAllocDefault));
+  memset(c->h_flags, 0, 64);
 
   // K2 shared-memory budget
   uint32_t maxw = 0, maxh = 0, maxcols = 0;
@@ -652,6 +655,7 @@ void rb_destroy(rb_ctx* c) {
   if (c->ev_entry) cudaEventDestroy(c->ev_entry);
   for (int i = 0; i < 2; ++i)
     if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -1038,7 +1042,11 @@ int rb_fetch_offsets(rb_ctx* c, rb_offset* out, size_t n_pairs) {
   RB_CUDA(c, cudaSetDevice(c->device));
   if (n_pairs)
     RB_CUDA(c, cudaMemcpyAsync(out, c->d_offsets + c->reg_first, n_pairs * sizeof(rb_offset), cudaMemcpyDeviceToHost, c->stream));
+  // the pipelined matcher's error word (a TMA transaction that never completed) travels with the offsets: results
+  // computed from an incomplete tile must not be reported as RB_OK
+  if (c->d_work && c->h_flags) RB_CUDA(c, cudaMemcpyAsync(c->h_flags, c->d_work, 16, cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->d_work && c->h_flags && c->h_flags[2]) { c->err = "pipelined matcher: a TMA transaction timed out"; return RB_ERR_CUDA; }
   return RB_OK;
 }
 
@@ -1319,8 +1327,7 @@ int rb_filter_fragment(rb_ctx* c, const rb_placement* placements, size_t n, uint
   }
   const size_t fwords = (size_t)g.H * c->fg_NW;
   if (n > c->fg_cap) {
-    for (auto& kv : c->ipc_open) cudaIpcCloseMemHandle(kv.second);
-  cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred);
+    cudaFree(c->d_fgbits); cudaFree(c->d_fg_nkept); cudaFree(c->d_fg_deferred);
     c->bytes -= c->fg_cap * (fwords * 4 + 8);
     c->d_fgbits = c->d_fg_nkept = c->d_fg_deferred = nullptr;
     c->fg_cap = 0;
@@ -1461,6 +1468,7 @@ int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, 
   RS_CUDA(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
   const size_t px = (size_t)W * H, words = (size_t)H * g.NS;
   uint16_t* d_dots = nullptr;
+  struct DotsGuard { uint16_t*& p; ~DotsGuard() { if (p) cudaFree(p); p = nullptr; } } dots_guard{d_dots};  // freed on every exit path
   RS_CUDA(s, cudaMalloc(&d_dots, px * 32));
   RS_CUDA(s, cudaMalloc(&s->d_image, g.frame_stride + 256));
   RS_CUDA(s, cudaMalloc(&s->d_mask, px + 256));
@@ -1493,6 +1501,7 @@ int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, 
   RS_CUDA(s, cudaMemcpyAsync(&n, s->d_count, 8, cudaMemcpyDeviceToHost, s->stream));
   RS_CUDA(s, cudaStreamSynchronize(s->stream));
   cudaFree(d_dots);
+  d_dots = nullptr;
   s->nkp = (uint32_t)n;
   RS_CUDA(s, cudaMalloc(&s->d_kps, ((size_t)n + 1) * sizeof(RbSnipKp)));
   uint32_t* cnt = reinterpret_cast<uint32_t*>(s->d_count + 1);
@@ -1639,6 +1648,7 @@ int rb_aws_compare(rb_ctx* c, size_t first, size_t n, uint8_t* heat, uint32_t* f
     RB_CUDA(c, dmalloc(c, &c->d_map, need));
     c->map_cap = need;
   }
+  c->map_w = c->map_h = 0;  // the scratch no longer holds a fragment map (rb_map_device / rb_blend_map must not serve it)
   uint32_t* d_fc = reinterpret_cast<uint32_t*>(c->d_map);
   uint8_t* d_heat = c->d_map + px * 4;
   if (heat) RB_CUDA(c, cudaMemcpyAsync(d_heat, heat, px, cudaMemcpyHostToDevice, c->stream));

@@ -185,6 +185,9 @@ def reduce_fragment_map_fused(reg, group=None, dst: int = 0, want_dots: bool = T
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     if handles is None:
         handles = exchange_map_handles(reg, group)
+    # every rank's blit (blit_blend / filter_fragment waits for its own stream) must have finished before a peer
+    # reads its map over IPC; with cached handles nothing else orders that
+    dist.barrier(group=group)
     out = None
     if world <= 2:  # one kernel on the destination rank: the only peer's map crosses the link once
         if rank == dst:

@@ -55,7 +55,20 @@ def _worker(rank, world, port, n_frames, backend, q):
             pl = np.zeros(len(own), PLACEMENT_DTYPE)
             pl["frame"], pl["x"], pl["y"] = own - first, pos[own, 1] - zx, pos[own, 2] - zy
             reg.blit_blend(pl, mw, mh, want_dots=False)
-            fused = shard.reduce_fragment_map_fused(reg)          # one kernel over the peers' maps (CUDA IPC)
+            handles = shard.exchange_map_handles(reg)
+            fused = shard.reduce_fragment_map_fused(reg, handles=handles)  # one kernel over the peers' maps (CUDA IPC)
+            # a pass-2 call with few frames, then one with more (its foreground store grows), between two fused
+            # reductions that reuse the cached handles: the peers' map mappings must survive the growth
+            half = max(len(pl) // 2, 1)
+            reg.filter_fragment(pl[:half], mw, mh, background=np.zeros((mh, mw), np.uint8), want_dots=False)
+            shard.reduce_fragment_map_fused(reg, handles=handles)
+            reg.filter_fragment(pl, mw, mh, background=np.zeros((mh, mw), np.uint8), want_dots=False)
+            shard.reduce_fragment_map_fused(reg, handles=handles)
+            reg.blit_blend(pl, mw, mh, want_dots=False)
+            again = shard.reduce_fragment_map_fused(reg, handles=handles)
+            if rank == 0:
+                for a, b in zip(fused, again):
+                    assert np.array_equal(a, b), "fused reduction after the foreground store grew differs"
             reg.blit_blend(pl, mw, mh, want_dots=False)          # the partial map again: rank 0's now holds the sum
             plain = shard.reduce_fragment_map(reg)
             if rank == 0:

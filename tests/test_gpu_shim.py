@@ -59,6 +59,14 @@ def test_collector_shim_with_gpu_map_assembly(batch, tmp_path):
     assert "dots from rb_blit_blend" in out and int(out.split()[1]) >= 2, out
 
 
+def test_collector_shim_gpu_blit_with_keys_across_batches(tmp_path):
+    """gpu_blit + fill_keys with a batch smaller than the sequence: from the second batch on a frame's store slot
+    differs from its index in the batch; the kpr::grid handed to the callback must still be that frame's."""
+    seq = synth.scrolling_tilemap(40, 320, 224, seed=17)
+    out = _run(seq.frames, 9, True, str(tmp_path), gpu_blit=True)
+    assert "keys compared" in out and "dots from rb_blit_blend" in out, out
+
+
 def test_filter_shim_matches_reference_fdf_filter(tmp_path):
     """include/fdf_b200.hpp (rb_filter_fragment) against the reference's fdf::filter on the reference
     collector's own fragments: filtered dots, frame lists and every fde::mask handed to the callback."""
