@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RB_ABI_VERSION 3
+#define RB_ABI_VERSION 4
 
 typedef enum rb_status {
   RB_OK = 0,
@@ -63,6 +63,8 @@ typedef struct rb_config {
   uint32_t overlap_batches; /* 0 = auto (1 = K1 then matcher, one after the other); > 1: batches per call, K1 of
                                batch b + 1 on a second stream concurrently with the matcher of batch b (slower
                                on B200 as measured; kept for experiments)                                     */
+  uint32_t host_threads;    /* 0 = auto; host threads of rb_register_host_async's packer (auto: processors /
+                               max(ranks on this node, contexts of this process))                            */
 } rb_config;
 
 /* == std::optional<cdt::offset_t> returned by kpm::match (src/kpm.hpp:395-415), plus flags. */
@@ -98,7 +100,11 @@ typedef struct rb_region_vote {
   uint32_t nticket;          /* min(region_votes, nbins)                           */
   rb_bin ticket[4];          /* count desc, dx asc, dy asc                         */
   uint32_t ngt[4], nge[4];   /* #bins with count > / >= ticket[k].count            */
+  uint32_t hist_hash;        /* digest of the whole histogram (totalizator_t, src/kpm.hpp:70-76): wrapping sum over
+                                its bins of the bin digest below                    */
 } rb_region_vote;
+/* bin digest: h = (dx & 0xFFFF) | dy << 16; h = h * 0x9E3779B1 ^ count * 0x85EBCA77; h ^= h >> 15; h *= 0x2C1B3C6D;
+ * h ^= h >> 12; h *= 0x297A2D39; h ^= h >> 15   (all uint32, wrapping) */
 
 void rb_default_config(rb_config* cfg, uint32_t width, uint32_t height, uint32_t max_frames);
 
@@ -123,6 +129,15 @@ int rb_register_async(rb_ctx* ctx, size_t first, size_t n);
  * `frames` must stay valid until the next synchronising call (rb_fetch_*, rb_synchronize); pinned
  * memory (rb_alloc_host) is what makes the copies overlap. */
 int rb_register_host_async(rb_ctx* ctx, const uint8_t* frames, size_t first, size_t n);
+/* How the chunks travel is decided per chunk from measured rates: host threads pack a chunk
+ * to 4 bit/pixel (half the bytes cross PCIe), or -- page-locked `frames` only -- the chunk is copied as it is and
+ * packed on the device; both lanes work at the same time.  rb_host_lane_stats reports the last call's split. */
+int rb_host_lane_stats(rb_ctx* ctx, uint64_t* raw_chunks, uint64_t* packed_chunks, double* link_GBps, double* pack_fps,
+                       int* threads);
+/* The same for a caller that already holds 4 bit/pixel frames (the layout a packed capture would have: pixel x in
+ * nibble x & 1 of byte x >> 1; rows of row_bytes >= ceil(W / 2) bytes, frames back to back): one copy per chunk,
+ * no host work. */
+int rb_register_host_packed4(rb_ctx* ctx, const uint8_t* packed, size_t row_bytes, size_t first, size_t n);
 
 /* Copies the n-1 pair results of the last rb_register_async to the host and waits for them.
  * out[i] belongs to frames (first+i, first+i+1). */

@@ -20,7 +20,7 @@ KP_DTYPE = np.dtype([("code", "u1", (13,)), ("weight", "u1"), ("x", "<u2"), ("y"
 BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
 VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
                        ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
-                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,))])
+                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,)), ("hist_hash", "<u4")])
 RESULT_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("valid", "<u4"), ("tie_sensitive", "<u4"),
                          ("active", "<u4"), ("top_dx", "<i4", (2,)), ("top_dy", "<i4", (2,)),
                          ("top_score", "<u4", (2,)), ("ntop", "<u4")])

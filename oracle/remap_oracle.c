@@ -48,7 +48,16 @@ typedef struct {
   ro_bin ticket[4];        /* defined order: cnt desc, dx asc, dy asc                              */
   uint32_t ngt[4];         /* #bins with cnt >  ticket[k].cnt                                      */
   uint32_t nge[4];         /* #bins with cnt >= ticket[k].cnt (includes ticket[k])                 */
+  uint32_t hist_hash;      /* wrapping sum over all bins of ro_bin_hash (digest of the whole histogram)   */
 } ro_region_vote;
+
+/* Digest of one bin of kpm's totalizator_t (src/kpm.hpp:70-76); defined in include/remap_b200.h. */
+static uint32_t ro_bin_hash(int32_t dx, int32_t dy, uint32_t cnt) {
+  uint32_t h = ((uint32_t)dx & 0xFFFFu) | ((uint32_t)dy << 16);
+  h = h * 0x9E3779B1u ^ cnt * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
 
 typedef struct {
   int32_t dx, dy;
@@ -279,6 +288,7 @@ static void ro_region(const ro_config* cfg, const ro_keypoint* prev, size_t np, 
     i = j;
   }
   out->nbins = (uint32_t)nb;
+  for (size_t i = 0; i < nb; ++i) out->hist_hash += ro_bin_hash(all[i].dx, all[i].dy, all[i].cnt);
   if (bins_out)
     for (size_t i = 0; i < nb && i < bins_cap; ++i) bins_out[i] = all[i];
   out->nticket = nb < rv ? (uint32_t)nb : rv;

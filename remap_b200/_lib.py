@@ -25,6 +25,7 @@ SYMBOLS = [
     "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count", "rb_register_host_async", "rb_blit_blend",
     "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
     "rb_aws_compare", "rb_map_device", "rb_blend_map", "rb_map_export", "rb_blend_map_peers", "rb_sum_map_slice", "rb_blend_map_slices", "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
+    "rb_host_lane_stats", "rb_register_host_packed4",
 ]
 
 
@@ -34,7 +35,8 @@ class RbConfig(C.Structure):
                 ("device", C.c_int32), ("max_frames", C.c_uint32), ("compute_median", C.c_uint32),
                 ("code_slots", C.c_uint32), ("offset_slots", C.c_uint32), ("profile", C.c_uint32),
                 ("stream", C.c_void_p), ("kpm_mode", C.c_uint32), ("list_cap", C.c_uint32),
-                ("run_pairs", C.c_uint32), ("upload_chunk", C.c_uint32), ("overlap_batches", C.c_uint32)]
+                ("run_pairs", C.c_uint32), ("upload_chunk", C.c_uint32), ("overlap_batches", C.c_uint32),
+                ("host_threads", C.c_uint32)]
 
 
 class RemapLibraryMissing(RuntimeError):
@@ -71,6 +73,11 @@ def load(build_if_missing: bool = False):
     lib.rb_register_async.argtypes = [vp, sz, sz]
     lib.rb_register_host_async.restype = C.c_int
     lib.rb_register_host_async.argtypes = [vp, vp, sz, sz]
+    lib.rb_register_host_packed4.restype = C.c_int
+    lib.rb_register_host_packed4.argtypes = [vp, vp, sz, sz, sz]
+    lib.rb_host_lane_stats.restype = C.c_int
+    lib.rb_host_lane_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
     lib.rb_blit_blend.restype = C.c_int
     lib.rb_blit_blend.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp]
     lib.rb_filter_fragment.restype = C.c_int

@@ -18,7 +18,7 @@ PLACEMENT_DTYPE = np.dtype([("frame", "<u4"), ("x", "<i4"), ("y", "<i4")])
 BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
 VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
                        ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
-                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,))])
+                       ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,)), ("hist_hash", "<u4")])
 assert KEYPOINT_DTYPE.itemsize == 24 and OFFSET_DTYPE.itemsize == 12
 
 
@@ -37,7 +37,7 @@ class Registrar:
 
     def __init__(self, width, height, max_frames, device=0, compute_median=True, profile=False, stream=None,
                  code_slots=0, offset_slots=0, grid=(4, 2), overlap=16, weight_switch=10, region_votes=3,
-                 kpm_mode=0, list_cap=0, run_pairs=0, upload_chunk=0, overlap_batches=0):
+                 kpm_mode=0, list_cap=0, run_pairs=0, upload_chunk=0, overlap_batches=0, host_threads=0):
         self._lib = _lib.load()
         cfg = _lib.RbConfig()
         self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
@@ -50,6 +50,7 @@ class Registrar:
         cfg.stream = stream
         cfg.kpm_mode, cfg.list_cap, cfg.run_pairs, cfg.upload_chunk = kpm_mode, list_cap, run_pairs, upload_chunk
         cfg.overlap_batches = overlap_batches
+        cfg.host_threads = host_threads
         self.width, self.height, self.max_frames = width, height, max_frames
         self.nreg = grid[0] * grid[1]
         self._ctx = C.c_void_p()
@@ -103,6 +104,22 @@ class Registrar:
         assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width), frames.shape
         self._check(self._lib.rb_register_host_async(self._ctx, frames.ctypes.data_as(C.c_void_p), first, frames.shape[0]))
         self._keep = frames
+
+    def register_host_packed4(self, packed, first=0):
+        """register frames the caller holds as 4 bit/pixel: packed (n, H, row_bytes) uint8, pixel x in nibble x & 1
+        of byte x >> 1 (rb_register_host_packed4)."""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        assert packed.ndim == 3 and packed.shape[1] == self.height and packed.shape[2] >= (self.width + 1) // 2, packed.shape
+        self._check(self._lib.rb_register_host_packed4(self._ctx, packed.ctypes.data_as(C.c_void_p), packed.shape[2], first,
+                                                       packed.shape[0]))
+        self._keep = packed
+
+    @property
+    def host_lane_stats(self):
+        """Last register_host_async: chunks sent raw / packed, and the measured rates behind the choice."""
+        raw, pk, link, fps, th = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_double(), C.c_int()
+        self._check(self._lib.rb_host_lane_stats(self._ctx, C.byref(raw), C.byref(pk), C.byref(link), C.byref(fps), C.byref(th)))
+        return dict(raw_chunks=raw.value, packed_chunks=pk.value, link_GBps=link.value, pack_fps=fps.value, threads=th.value)
 
     def fetch_offsets(self, n_pairs, out=None):
         if out is None:

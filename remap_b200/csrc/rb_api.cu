@@ -8,7 +8,9 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <new>
+#include <time.h>
 #include <string>
 #include <utility>
 #include <vector>
@@ -19,6 +21,7 @@
 #include "rb_kpe.cuh"
 #include "rb_kpm.cuh"
 #include "rb_kpm_fast.cuh"
+#include "rb_kpm_big.cuh"
 #include "rb_prep.cuh"
 #include "rb_blit.cuh"
 #include "rb_fg.cuh"
@@ -313,8 +316,9 @@ struct rb_ctx {
   uint2* d_counts;       // [frame][region] (n_all, n_w2)
   uint2* d_deferred;     // [pair][region] worst case: what the first matcher pass deferred
   uint2* d_deferred2;    // ... and what the second, large-list pass deferred (general kernel)
-  RbKpmFastParams fast2; // second pass: one CTA per SM, lists up to ~2,000 entries, one pair per work item
-  size_t fast2_smem;
+  RbKpmFastParams big;   // rb_kpm_big_kernel: one CTA per SM, lists of thousands of entries.  Second pass over what the
+  size_t big_smem;       //   first-pass kernel deferred (one pair per work item), or -- large regions -- THE matcher
+  bool big_primary;
   uint32_t* d_work;      // [0] work-item counter, [1] deferred count
   CUtensorMap tmap;      // 3-D tensor map of d_frames4: (row bytes, rows, frames)
   RbKpmFastParams fast;  // geometry-dependent constants of the pipelined matcher
@@ -368,6 +372,12 @@ struct rb_ctx {
   cudaEvent_t ev_copy[2], ev_entry;
   uint8_t* h_stage[2];     // pinned staging: two chunks of packed 4 bit/pixel frames
   uint32_t* h_flags;       // pinned: copy of d_work[0..3] fetched with the offsets ([2] = matcher error word)
+  // rb_register_host_async: one "landed" event per chunk (timing enabled: the link rate is estimated from them)
+  std::vector<cudaEvent_t> ev_chunk, ev_chunk_start;
+  double link_Bps;         // estimated host -> device rate of this context's link (bytes / s)
+  double pack_fps;         // estimated rate of the host packer (frames / s)
+  uint64_t lane_raw, lane_packed;  // chunks of the last rb_register_host_async call that went raw / packed
+  int host_threads;        // packer threads of this context
   size_t stage_frames;
   uint64_t launches;
   bool debug_sync;
@@ -401,6 +411,8 @@ static uint32_t next_pow2(uint32_t v) {
   while (p < v) p <<= 1;
   return p;
 }
+
+static std::atomic<int> g_live_contexts{0};  // contexts alive in this process (host packer thread share)
 
 template <typename T>
 static cudaError_t dmalloc(rb_ctx* c, T** p, size_t bytes) {
@@ -441,10 +453,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
   c->device = cfg->device;
   c->debug_sync = getenv("RB_DEBUG_SYNC") != nullptr;
   c->k3_reference = getenv("RB_K3_REFERENCE") != nullptr;
-  {  // host packer threads: this process's fair share of the host when there is one process per GPU
-    const long procs = sysconf(_SC_NPROCESSORS_ONLN);
-    rb_hostpack_set_threads((int)(procs > 0 ? (procs / ndev > 0 ? procs / ndev : 1) : 1));
-  }
+  ++g_live_contexts;
   *out = c;  // returned even on failure so that rb_last_error can be read; caller rb_destroy()s it
   if (cfg->max_frames < 2) { c->err = "max_frames must be >= 2"; return RB_ERR_INVALID; }
   if (rb_make_geom(cfg->width, cfg->height, cfg->grid_w, cfg->grid_h, cfg->overlap, cfg->weight_switch,
@@ -561,33 +570,77 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     int smem_max = 0;
     RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->fast_smem = rbf::smem_bytes(f);
-    const bool fast_ok = cap >= 16 && bx <= 256 && f.box_y <= 256 && c->fast_smem <= (size_t)smem_max && g.W < 16384 && g.H < 4096 &&
-                         f.offbits <= 24 && f.run <= 1024 && maxcols * maxh < 65536 &&
-                         (g.W << dybits) < (1u << 28);
-    if (!fast_ok && cfg->kpm_mode == 0) c->cfg.kpm_mode = 1;  // geometry outside the pipelined matcher's limits
-    if (c->cfg.kpm_mode == 0) {
-      RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fast_smem));
-      int occ = 0;
-      RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_kpm_fast_kernel, RB_FAST_NT, c->fast_smem));
-      c->fast_ctas_per_sm = occ < 1 ? 1 : occ;
+    const bool tma_ok = bx <= 256 && f.box_y <= 256 && g.W < 16384 && g.H < 4096 && f.run <= 1024;
+    bool fast_ok = tma_ok && cap >= 16 && c->fast_smem <= (size_t)smem_max && f.offbits <= 24 && maxcols * maxh < 65536 &&
+                   (g.W << dybits) < (1u << 28);
+    // ---- the large-region matcher (rb_kpm_big.cuh): region-relative offsets, 6 bytes per keypoint and frame ------
+    RbKpmFastParams& B = c->big;
+    B = f;
+    bool big_ok = tma_ok;
+    {
+      uint32_t lxmax = 0;
+      for (uint32_t s = 0; s < g.grid_w; ++s) {
+        const uint32_t tx0 = (g.col0[s] - 2) & ~31u;
+        if (g.col1[s] - 3 - tx0 > lxmax) lxmax = g.col1[s] - 3 - tx0;
+      }
+      uint32_t dxb = 0, dyb = 0;
+      while ((1u << dxb) <= 2 * maxcols) ++dxb;
+      while ((1u << dyb) <= 2 * maxh) ++dyb;
+      B.dybits = dyb;
+      B.offbits = dxb + dyb;
+      B.bias_x = maxcols;
+      B.bias_y = maxh;
+      big_ok = big_ok && lxmax <= 255 && maxh <= 256 && B.offbits <= 19;  // 16-bit positions; >= 13 bits of count per bin
+      const uint32_t cntmax_b = (1u << (32 - B.offbits)) - 1u;
+      B.oslots = 2048;
+      B.cap = 0;
+      // the largest bucket table whose lists still hold what a dense frame puts into a region (~ a keypoint per 6 pixels)
+      const uint32_t want = cfg->list_cap ? cfg->list_cap : maxcols * maxh / 6;
+      for (uint32_t ts = 8192; big_ok && ts >= 1024; ts >>= 1) {
+        B.tslots = ts;
+        B.cap = 0;
+        const size_t fixed = rbb::smem_bytes(B) + 16;
+        if (fixed >= (size_t)smem_max) continue;
+        uint32_t fit = (uint32_t)(((size_t)smem_max - fixed) / 12);
+        if (fit > 65532) fit = 65532;
+        if (fit > cntmax_b) fit = cntmax_b;
+        if (fit > 8 * ts) fit = 8 * ts;
+        fit &= ~3u;
+        B.cap = fit;
+        if (fit >= want || ts == 1024) break;
+      }
+      if (B.cap < 64) big_ok = false;
+    }
+    // Which kernel takes the regions first: rb_kpm_fast_kernel (two CTAs per SM, full codes in shared memory) where
+    // typical region lists fit its 1,280 entries; rb_kpm_big_kernel where a sparse frame already overflows them.
+    // kpm_mode: 0 = by region size, 1 = general kernel only, 2 = large-region kernel first, 3 = fast kernel first.
+    c->big_primary = big_ok && (cfg->kpm_mode == 2 || (cfg->kpm_mode == 0 && maxcols * maxh > 24000) || !fast_ok);
+    if (cfg->kpm_mode == 3 && fast_ok) c->big_primary = false;
+    if (!fast_ok && !big_ok) c->cfg.kpm_mode = 1;  // geometry outside both pipelined matchers' limits
+    if (c->cfg.kpm_mode != 1) {
+      c->cfg.kpm_mode = 0;
+      if (c->big_primary) {
+        B.lcap = B.cap;  // one row length for K1c and the matcher
+        f.lcap = B.lcap;
+      } else {
+        if (B.cap > f.lcap) B.cap = f.lcap & ~3u;  // second pass: bounded by the list rows K1c writes
+        B.lcap = f.lcap;
+        if (B.cap <= f.cap) big_ok = false;        // nothing to gain
+      }
+      c->big_smem = big_ok ? rbb::smem_bytes(B) : 0;
+      if (c->big_smem)
+        RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->big_smem));
+      if (!c->big_primary) {
+        RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->fast_smem));
+        int occ = 0;
+        RB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rb_kpm_fast_kernel, RB_FAST_NT, c->fast_smem));
+        c->fast_ctas_per_sm = occ < 1 ? 1 : occ;
+      }
       RB_CUDA(c, dmalloc(c, &c->d_frames4, c->frame_stride4 * N + 256));
       RB_CUDA(c, dmalloc(c, &c->d_lists, (size_t)N * g.nreg * f.lcap * 4 + 256));
       RB_CUDA(c, dmalloc(c, &c->d_counts, (size_t)N * g.nreg * sizeof(uint2)));
       RB_CUDA(c, dmalloc(c, &c->d_deferred, (size_t)N * g.nreg * sizeof(uint2)));
       RB_CUDA(c, dmalloc(c, &c->d_deferred2, (size_t)N * g.nreg * sizeof(uint2)));
-      // second pass for regions whose lists do not fit the first: the same kernel with the largest lists
-      // one CTA can hold (capped by the list rows, the 11-bit entry index and the bin count field)
-      c->fast2 = f;
-      uint32_t cap2 = f.lcap < 2044 ? f.lcap : 2044;
-      if (cap2 > cntmax) cap2 = cntmax;
-      cap2 &= ~3u;
-      c->fast2.cap = cap2;
-      c->fast2.tslots = next_pow2(cap2 < 64 ? 64 : cap2);
-      c->fast2.oslots = 2048;
-      c->fast2_smem = rbf::smem_bytes(c->fast2);
-      if (cap2 <= cap || c->fast2_smem > (size_t)smem_max) c->fast2_smem = 0;  // no second pass
-      RB_CUDA(c, cudaFuncSetAttribute(rb_kpm_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(c->fast2_smem > c->fast_smem ? c->fast2_smem : c->fast_smem)));
       RB_CUDA(c, dmalloc(c, &c->d_work, 256));
       RB_CUDA(c, cudaMemsetAsync(c->d_frames4, 0, c->frame_stride4 * N + 256, c->stream));
       RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 256, c->stream));
@@ -657,7 +710,10 @@ void rb_destroy(rb_ctx* c) {
     if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (auto e : c->ev_chunk) cudaEventDestroy(e);
+  for (auto e : c->ev_chunk_start) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  --g_live_contexts;
   delete c;
 }
 
@@ -835,44 +891,57 @@ static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cu
       }
       if (ev) RB_CUDA(c, cudaEventRecord(ev[3], c->stream));
       RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));  // work counter; deferred count / error word accumulate
-      RbKpmFastParams f = c->fast;
-      f.lists = c->d_lists;
-      f.counts = c->d_counts;
-      f.votes = p.votes;
-      f.first_frame = (uint32_t)first;
-      f.npairs = (uint32_t)(n - 1);
-      f.work_counter = c->d_work;
-      f.deferred_count = c->d_work + 4;  // per-launch list position; d_work[1] keeps the running total
-      f.deferred = c->d_deferred;
-      f.deferred_cap = (uint32_t)((n - 1) * g.nreg);
-      f.items = nullptr; f.nitems = nullptr;
+      const uint32_t dcap = (uint32_t)((n - 1) * g.nreg);
+      auto fill = [&](RbKpmFastParams& q) {
+        q.lists = c->d_lists; q.counts = c->d_counts; q.votes = p.votes;
+        q.first_frame = (uint32_t)first; q.npairs = (uint32_t)(n - 1);
+        q.work_counter = c->d_work;
+        q.deferred_cap = dcap;
+      };
       RB_CUDA(c, cudaMemsetAsync(c->d_work + 4, 0, 4, c->stream));
-      const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
-      uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
-      if (grid > witems) grid = witems;
-      rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
-      RB_LAUNCHED(c, "rb_kpm_fast_kernel");
-      if (ev) RB_CUDA(c, cudaEventRecord(ev[4], c->stream));
       const uint2* glist = c->d_deferred;
       const uint32_t* gcount = c->d_work + 4;
-      if (c->fast2_smem) {  // second pass over what the first deferred (exits at once on an empty list)
-        RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));
-        RB_CUDA(c, cudaMemsetAsync(c->d_work + 5, 0, 4, c->stream));
-        RbKpmFastParams f2 = c->fast2;
-        f2.lists = c->d_lists; f2.counts = c->d_counts; f2.votes = p.votes;
-        f2.first_frame = (uint32_t)first; f2.npairs = (uint32_t)(n - 1);
-        f2.items = c->d_deferred; f2.nitems = c->d_work + 4;
-        f2.work_counter = c->d_work;
-        f2.deferred_count = c->d_work + 5;
-        f2.deferred = c->d_deferred2;
-        f2.deferred_cap = f.deferred_cap;
-        uint32_t grid2 = (uint32_t)c->sm_count;
-        if (grid2 > f.deferred_cap) grid2 = f.deferred_cap;
-        rb_kpm_fast_kernel<<<grid2, RB_FAST_NT, c->fast2_smem, c->stream>>>(c->tmap, f2);
-        RB_LAUNCHED(c, "rb_kpm_fast_kernel (second pass)");
-        glist = c->d_deferred2;
-        gcount = c->d_work + 5;
+      if (c->big_primary) {  // large regions: K2b over runs of pairs, one CTA per SM
+        RbKpmFastParams f = c->big;
+        fill(f);
+        f.deferred_count = c->d_work + 4;  // per-launch list position; d_work[1] keeps the running total
+        f.deferred = c->d_deferred;
+        f.items = nullptr; f.nitems = nullptr;
+        const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
+        uint32_t grid = (uint32_t)c->sm_count;
+        if (grid > witems) grid = witems;
+        rb_kpm_big_kernel<<<grid, RB_BIG_NT, c->big_smem, c->stream>>>(c->tmap, f);
+        RB_LAUNCHED(c, "rb_kpm_big_kernel");
+        if (ev) RB_CUDA(c, cudaEventRecord(ev[4], c->stream));
+      } else {
+        RbKpmFastParams f = c->fast;
+        fill(f);
+        f.deferred_count = c->d_work + 4;
+        f.deferred = c->d_deferred;
+        f.items = nullptr; f.nitems = nullptr;
+        const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
+        uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
+        if (grid > witems) grid = witems;
+        rb_kpm_fast_kernel<<<grid, RB_FAST_NT, c->fast_smem, c->stream>>>(c->tmap, f);
+        RB_LAUNCHED(c, "rb_kpm_fast_kernel");
+        if (ev) RB_CUDA(c, cudaEventRecord(ev[4], c->stream));
+        if (c->big_smem) {  // second pass over what the first deferred (exits at once on an empty list)
+          RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 4, c->stream));
+          RB_CUDA(c, cudaMemsetAsync(c->d_work + 5, 0, 4, c->stream));
+          RbKpmFastParams f2 = c->big;
+          fill(f2);
+          f2.items = c->d_deferred; f2.nitems = c->d_work + 4;
+          f2.deferred_count = c->d_work + 5;
+          f2.deferred = c->d_deferred2;
+          uint32_t grid2 = (uint32_t)c->sm_count;
+          if (grid2 > dcap) grid2 = dcap;
+          rb_kpm_big_kernel<<<grid2, RB_BIG_NT, c->big_smem, c->stream>>>(c->tmap, f2);
+          RB_LAUNCHED(c, "rb_kpm_big_kernel (second pass)");
+          glist = c->d_deferred2;
+          gcount = c->d_work + 5;
+        }
       }
+      const struct { uint32_t deferred_cap; } f = {dcap};
       uint32_t dgrid = (uint32_t)c->sm_count * 2;
       if (dgrid > f.deferred_cap) dgrid = f.deferred_cap;
       rb_kpm_deferred_kernel<<<dgrid, c->kpm_nt, c->kpm_smem, c->stream>>>(p, glist, gcount, f.deferred_cap, c->d_work + 1);
@@ -957,56 +1026,23 @@ int rb_register_async(rb_ctx* c, size_t first, size_t n) {
   return RB_OK;
 }
 
-// rb_upload + rb_register_async in one call, pipelined three deep: host threads pack chunk k + 1 to
-// 4 bit/pixel in pinned staging (half the bytes cross PCIe) while chunk k is on the bus (second stream)
-// and chunk k - 1 is being registered (with the last frame of its predecessor as its first `previous`).
-int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
-  if (!c || !frames) return RB_ERR_INVALID;
-  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
-  RB_CUDA(c, cudaSetDevice(c->device));
-  const RbGeom& g = c->g;
-  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 1024;
-  const bool packed = c->d_frames4 != nullptr;  // the 4 bit/pixel store exists: ship frames packed
-  if (packed && c->stage_frames < chunk) {
-    for (int i = 0; i < 2; ++i) {
-      if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
-      RB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage[i]), c->frame_stride4 * chunk, cudaHostAllocDefault));
-    }
-    c->stage_frames = chunk;
-  }
-  // the copies must not overtake earlier work on the main stream that still reads these slots
-  RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
-  RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
-  if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));
-  size_t k = 0;
-  for (size_t at = 0; at < n; at += chunk, ++k) {
-    const size_t m = at + chunk < n ? chunk : n - at;
-    int rc;
-    if (packed) {
-      if (k >= 2) RB_CUDA(c, cudaEventSynchronize(c->ev_copy[k & 1]));  // staging buffer k & 1 is free again
-      rb_hostpack_frames(frames + (size_t)g.W * g.H * at, g.W, g.H, m, c->h_stage[k & 1], c->pitch4);
-      RB_CUDA(c, cudaMemcpyAsync(c->d_frames4 + c->frame_stride4 * (first + at), c->h_stage[k & 1], c->frame_stride4 * m,
-                                 cudaMemcpyHostToDevice, c->copy_stream));
-    } else {
-      rc = copy_frames(c, frames + (size_t)g.W * g.H * at, first + at, m, c->copy_stream);
-      if (rc != RB_OK) return rc;
-    }
-    RB_CUDA(c, cudaEventRecord(c->ev_copy[k & 1], c->copy_stream));
-    RB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copy[k & 1], 0));
-    if (packed) {  // K0u: the one-colour-per-byte store K1 reads
-      const uint64_t chunks16 = (uint64_t)m * g.H * (g.pitch / 16);
-      uint64_t blocks = (chunks16 + 255) / 256;
-      const uint64_t maxb = (uint64_t)c->sm_count * 16;
-      if (blocks > maxb) blocks = maxb;
-      rb_unpack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(c->d_frames4 + c->frame_stride4 * (first + at), c->pitch4,
-                                                               c->frame_stride4, c->d_frames + g.frame_stride * (first + at),
-                                                               g.pitch, g.frame_stride, g.H, (uint32_t)m);
-      RB_LAUNCHED(c, "rb_unpack_kernel");
-    }
-    if (first + at + m > c->uploaded) c->uploaded = first + at + m;
-    rc = at == 0 ? enqueue_range(c, first, m, first) : enqueue_range(c, first + at - 1, m + 1, first + at);
-    if (rc != RB_OK) return rc;
-  }
+// Threads the host packer of one context may use: an explicit rb_config.host_threads / RB_HOST_THREADS, else this
+// context's fair share of the host: processors / max(ranks of this node (LOCAL_WORLD_SIZE, set by torchrun and
+// most launchers), contexts alive in this process).  NOT processors / visible GPUs: one rank on an 8-GPU node owns
+// the whole host.
+static int packer_threads(const rb_ctx* c) {
+  if (const char* e = getenv("RB_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return v; }
+  if (c->cfg.host_threads) return (int)c->cfg.host_threads;
+  long procs = sysconf(_SC_NPROCESSORS_ONLN);
+  if (procs < 1) procs = 1;
+  int share = g_live_contexts.load();
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > share) share = v; }
+  if (share < 1) share = 1;
+  const long nt = procs / share;
+  return (int)(nt > 0 ? nt : 1);
+}
+
+static void note_registered(rb_ctx* c, size_t first, size_t n) {
   c->reg_first = first;
   c->reg_n = n;
   if (c->med_hi == c->med_lo) { c->med_lo = first; c->med_hi = first + n; }
@@ -1014,6 +1050,201 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
     if (first < c->med_lo) c->med_lo = first;
     if (first + n > c->med_hi) c->med_hi = first + n;
   }
+}
+
+static int ensure_chunk_events(rb_ctx* c, size_t nchunks) {
+  while (c->ev_chunk.size() < nchunks) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    RB_CUDA(c, cudaEventCreate(&a));
+    RB_CUDA(c, cudaEventCreate(&b));
+    c->ev_chunk_start.push_back(a);
+    c->ev_chunk.push_back(b);
+  }
+  return RB_OK;
+}
+
+// device side of one landed chunk: the store the chunk did NOT arrive in is derived on the device (K0 / K0u), then
+// the chunk is registered with the last frame of its predecessor as its first `previous`
+static int chunk_landed(rb_ctx* c, size_t first, size_t at, size_t m, bool arrived_packed, cudaEvent_t landed) {
+  const RbGeom& g = c->g;
+  RB_CUDA(c, cudaStreamWaitEvent(c->stream, landed, 0));
+  if (arrived_packed) {  // K0u: the one-colour-per-byte store K1 reads
+    const uint64_t chunks16 = (uint64_t)m * g.H * (g.pitch / 16);
+    uint64_t blocks = (chunks16 + 255) / 256;
+    const uint64_t maxb = (uint64_t)c->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    rb_unpack_kernel<<<(uint32_t)blocks, 256, 0, c->stream>>>(c->d_frames4 + c->frame_stride4 * (first + at), c->pitch4,
+                                                             c->frame_stride4, c->d_frames + g.frame_stride * (first + at),
+                                                             g.pitch, g.frame_stride, g.H, (uint32_t)m);
+    RB_LAUNCHED(c, "rb_unpack_kernel");
+  } else {
+    const int rc = pack_frames(c, first + at, m);  // K0 (no-op without the 4 bit/pixel store)
+    if (rc != RB_OK) return rc;
+  }
+  if (first + at + m > c->uploaded) c->uploaded = first + at + m;
+  return at == 0 ? enqueue_range(c, first, m, first) : enqueue_range(c, first + at - 1, m + 1, first + at);
+}
+
+// rb_upload + rb_register_async in one call for frames in HOST memory, pipelined.  A chunk of frames reaches the
+// device through one of two lanes that work AT THE SAME TIME:
+//   packed  host threads pack the chunk to 4 bit/pixel in pinned staging (half the bytes cross PCIe), one
+//           cudaMemcpyAsync, K0u derives the byte store on the device;
+//   raw     one cudaMemcpyAsync of the caller's bytes as they are (no host work at all; needs page-locked memory),
+//           K0 derives the packed store on the device.
+// Which lane a chunk takes is decided when its turn comes, from measured rates: the calling thread packs
+// continuously; a chunk goes raw when the link would otherwise run dry before the packer could deliver it
+// (bytes still queued on the link / measured link rate < chunk frames / measured packer rate).  With many host threads per GPU nearly
+// everything goes packed (the link is the limit and packed halves its load); with few threads per GPU (one rank of
+// eight on a node) nearly everything goes raw.  Copies of later chunks run under the kernels of earlier ones.
+int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
+  if (!c || !frames) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const RbGeom& g = c->g;
+  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 1024;
+  // Chunk sizes: `chunk` frames each, but a long call ramps up (128, 256, ... frames) and down again, so that the
+  // link starts after packing 128 frames, not 1,024, and the last copy + kernels that nothing overlaps are short.
+  std::vector<size_t> sizes;
+  {
+    std::vector<size_t> ramp;
+    size_t ramp_sum = 0;
+    if (chunk >= 256 && n >= 6 * chunk)
+      for (size_t r = 128; r < chunk; r *= 2) { ramp.push_back(r); ramp_sum += r; }
+    for (size_t r : ramp) sizes.push_back(r);
+    for (size_t left = n - 2 * ramp_sum; left > 0;) { const size_t m = left < chunk ? left : chunk; sizes.push_back(m); left -= m; }
+    for (size_t i = ramp.size(); i-- > 0;) sizes.push_back(ramp[i]);
+  }
+  const size_t nchunks = sizes.size();
+  const bool have4 = c->d_frames4 != nullptr;  // the 4 bit/pixel store exists: frames may travel packed
+  bool pinned = false;
+  {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, frames) == cudaSuccess) pinned = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  int lane_force = 0;  // RB_HOST_LANE=raw|packed: experiments and tests
+  if (const char* e = getenv("RB_HOST_LANE")) lane_force = !strcmp(e, "raw") ? 1 : !strcmp(e, "packed") ? 2 : 0;
+  if (have4 && c->stage_frames < chunk) {  // (no chunk is larger than `chunk`)
+    for (int i = 0; i < 2; ++i) {
+      if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
+      RB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage[i]), c->frame_stride4 * chunk, cudaHostAllocDefault));
+    }
+    c->stage_frames = chunk;
+  }
+  int rc = ensure_chunk_events(c, nchunks);
+  if (rc != RB_OK) return rc;
+  const int pack_threads = packer_threads(c);
+  // the copies must not overtake earlier work on the main stream that still reads these slots
+  RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
+  RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
+  if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));
+  c->lane_raw = c->lane_packed = 0;
+  const double raw_bytes_pf = (double)g.W * g.H, packed_bytes_pf = (double)c->frame_stride4;
+  size_t oldest = 0;          // first chunk whose copy may still be in flight
+  double inflight_bytes = 0;  // bytes queued on the link and not yet known to have landed
+  std::vector<double> chunk_bytes(nchunks, 0.0);
+  int stage_owner[2] = {-1, -1};  // chunk whose packed copy last read staging buffer i
+  int stage_next = 0;
+  size_t at = 0;
+  for (size_t k = 0; k < nchunks; at += sizes[k], ++k) {
+    const size_t m = sizes[k];
+    // retire landed copies; every retired copy refines the link estimate
+    while (oldest < k && cudaEventQuery(c->ev_chunk[oldest]) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->ev_chunk_start[oldest], c->ev_chunk[oldest]) == cudaSuccess && ms > 0.02f) {
+        const double bps = chunk_bytes[oldest] / (ms * 1e-3);
+        c->link_Bps = c->link_Bps > 0 ? 0.7 * c->link_Bps + 0.3 * bps : bps;
+      }
+      inflight_bytes -= chunk_bytes[oldest];
+      ++oldest;
+    }
+    cudaGetLastError();  // cudaErrorNotReady from the query is not an error
+    bool raw;
+    if (!have4) raw = true;
+    else if (lane_force) raw = lane_force == 1;
+    else if (!pinned) raw = false;  // pageable memory: the driver would stage it through its own bounce buffer
+    else {
+      const double link = c->link_Bps > 0 ? c->link_Bps : 50e9, pack = c->pack_fps > 0 ? c->pack_fps : 1e6;
+      // the packer delivers its next chunk to the link in t_pack; if the link's backlog runs out before that, the
+      // link would idle: give it this chunk as it is and let the packer start on the next one right away
+      // -- unless packed traffic alone already fills the link: then a raw chunk (twice the bytes) only sets it back
+      const double t_left = inflight_bytes / link, t_pack = m / pack;
+      raw = t_left < t_pack && pack * packed_bytes_pf < 0.85 * link;
+    }
+    cudaEvent_t landed = c->ev_chunk[k];
+    if (raw) {
+      RB_CUDA(c, cudaEventRecord(c->ev_chunk_start[k], c->copy_stream));
+      rc = copy_frames(c, frames + (size_t)g.W * g.H * at, first + at, m, c->copy_stream);
+      if (rc != RB_OK) return rc;
+      chunk_bytes[k] = m * raw_bytes_pf;
+      ++c->lane_raw;
+    } else {
+      const int sb = stage_next;
+      stage_next ^= 1;
+      if (stage_owner[sb] >= 0) RB_CUDA(c, cudaEventSynchronize(c->ev_chunk[stage_owner[sb]]));  // staging buffer free again
+      timespec t0, t1;
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      rb_hostpack_frames(frames + (size_t)g.W * g.H * at, g.W, g.H, m, c->h_stage[sb], c->pitch4, pack_threads);
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+      if (dt > 0) { const double fps = m / dt; c->pack_fps = c->pack_fps > 0 ? 0.7 * c->pack_fps + 0.3 * fps : fps; }
+      RB_CUDA(c, cudaEventRecord(c->ev_chunk_start[k], c->copy_stream));
+      RB_CUDA(c, cudaMemcpyAsync(c->d_frames4 + c->frame_stride4 * (first + at), c->h_stage[sb], c->frame_stride4 * m,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+      stage_owner[sb] = (int)k;
+      chunk_bytes[k] = m * packed_bytes_pf;
+      ++c->lane_packed;
+    }
+    RB_CUDA(c, cudaEventRecord(landed, c->copy_stream));
+    inflight_bytes += chunk_bytes[k];
+    rc = chunk_landed(c, first, at, m, !raw, landed);
+    if (rc != RB_OK) return rc;
+  }
+  note_registered(c, first, n);
+  return RB_OK;
+}
+
+// The same for callers that already hold 4 bit/pixel frames (pixel x in nibble x & 1 of byte x >> 1, rows of
+// `row_bytes` >= ceil(W / 2) bytes, frames back to back): one copy per chunk, no host work.
+int rb_register_host_packed4(rb_ctx* c, const uint8_t* packed, size_t row_bytes, size_t first, size_t n) {
+  if (!c || !packed) return RB_ERR_INVALID;
+  if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host_packed4: frame range"; return RB_ERR_CAPACITY; }
+  if (!c->d_frames4) { c->err = "rb_register_host_packed4: this geometry has no 4 bit/pixel store (kpm_mode = 1)"; return RB_ERR_STATE; }
+  const RbGeom& g = c->g;
+  if (row_bytes < (g.W + 1) / 2) { c->err = "rb_register_host_packed4: row_bytes < ceil(W / 2)"; return RB_ERR_INVALID; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 1024;
+  int rc = ensure_chunk_events(c, (n + chunk - 1) / chunk);
+  if (rc != RB_OK) return rc;
+  RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));
+  RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
+  if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));
+  size_t k = 0;
+  for (size_t at = 0; at < n; at += chunk, ++k) {
+    const size_t m = at + chunk < n ? chunk : n - at;
+    RB_CUDA(c, cudaEventRecord(c->ev_chunk_start[k], c->copy_stream));
+    if (row_bytes == c->pitch4)
+      RB_CUDA(c, cudaMemcpyAsync(c->d_frames4 + c->frame_stride4 * (first + at), packed + row_bytes * g.H * at,
+                                 c->frame_stride4 * m, cudaMemcpyHostToDevice, c->copy_stream));
+    else  // the pad bytes of the device rows stay zero (rb_create clears the store)
+      RB_CUDA(c, cudaMemcpy2DAsync(c->d_frames4 + c->frame_stride4 * (first + at), c->pitch4, packed + row_bytes * g.H * at,
+                                   row_bytes, (g.W + 1) / 2, (size_t)g.H * m, cudaMemcpyHostToDevice, c->copy_stream));
+    RB_CUDA(c, cudaEventRecord(c->ev_chunk[k], c->copy_stream));
+    rc = chunk_landed(c, first, at, m, true, c->ev_chunk[k]);
+    if (rc != RB_OK) return rc;
+  }
+  note_registered(c, first, n);
+  return RB_OK;
+}
+
+// Last rb_register_host_async: chunks that went raw / packed, and the rate estimates the choice was made from.
+int rb_host_lane_stats(rb_ctx* c, uint64_t* raw_chunks, uint64_t* packed_chunks, double* link_GBps, double* pack_fps, int* threads) {
+  if (!c) return RB_ERR_INVALID;
+  if (raw_chunks) *raw_chunks = c->lane_raw;
+  if (packed_chunks) *packed_chunks = c->lane_packed;
+  if (link_GBps) *link_GBps = c->link_Bps / 1e9;
+  if (pack_fps) *pack_fps = c->pack_fps;
+  if (threads) *threads = packer_threads(c);
   return RB_OK;
 }
 

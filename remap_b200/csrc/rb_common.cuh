@@ -41,6 +41,7 @@ struct RbRegionVote {
   RbBin ticket[4];
   uint32_t ngt[4];
   uint32_t nge[4];
+  uint32_t hist_hash;  // order-independent digest of the whole offset histogram: sum of rb_bin_hash over its bins
 };
 
 // Result of one pair, mirrors ro_match_result.
@@ -67,6 +68,16 @@ struct RbGeom {
   // section s covers columns [col0[s], col1[s]) / rows [row0[s], row1[s])   
   uint32_t col0[8], col1[8], row0[8], row1[8];
 };
+
+// Digest of one offset-histogram bin; a region's hist_hash is the wrapping 32-bit SUM over its bins, so it does not
+// depend on the order bins are met in.  The full-sequence parity runs compare it with the same sum over the
+// reference's totalizator_t (oracle/ref_harness.cpp, digest mode).
+RB_HD uint32_t rb_bin_hash(int32_t dx, int32_t dy, uint32_t cnt) {
+  uint32_t h = ((uint32_t)dx & 0xFFFFu) | ((uint32_t)dy << 16);
+  h = h * 0x9E3779B1u ^ cnt * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
 
 RB_HD uint32_t rb_maj(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (a & c) | (b & c); }
 RB_HD uint32_t rb_xor3(uint32_t a, uint32_t b, uint32_t c) { return a ^ b ^ c; }

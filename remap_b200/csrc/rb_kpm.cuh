@@ -62,7 +62,7 @@ struct Smem {  // carved from dynamic shared memory, all uint32_t-aligned
 };
 enum {
   S_NPREV = 0, S_W2PREV, S_NCURR, S_W2CURR, S_NTOUCHED, S_OVERFLOW, S_NGT0, S_NGE0 = S_NGT0 + 3,
-  S_PFILL = S_NGE0 + 3, S_CFILL, S_NBAND, S_NCHUNK, S_COUNT
+  S_PFILL = S_NGE0 + 3, S_CFILL, S_NBAND, S_NCHUNK, S_HASH, S_COUNT
 };
 
 RB_HD size_t smem_words(const RbKpmParams& p, uint32_t NT) {
@@ -307,6 +307,7 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
                   if (tid < 6) s.scal[S_NGT0 + tid] = (sweep == 0) ? 0u : s.scal[S_NGT0 + tid];
                   if (tid < 3 && sweep == 0) s.best[tid] = 0;
                   if (tap && tid == 0 && sweep == 0 && q == 0) *p.tap_count = 0;
+                  if (tid == 0 && sweep == 0 && q == 0) s.scal[S_HASH] = 0;  // also after a restart
                 }
                 if (tid == 0) { s.scal[S_PFILL] = 0; s.scal[S_CFILL] = 0; }
               }
@@ -412,6 +413,15 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
           const uint32_t nt = s.scal[S_NTOUCHED];
           if (sweep == 0) {
             nbins += nt;
+            RB_FOR_THREADS(tid, NT) {  // digest of the histogram: every bin lives in exactly one partition
+              uint32_t hh = 0;
+              for (uint32_t i = tid; i < nt; i += NT) {
+                const uint32_t os = s.touched[i];
+                const RbBin b = sel_decode(sel_key(s.okey[os], s.ocnt[os]));
+                hh += rb_bin_hash(b.dx, b.dy, b.cnt);
+              }
+              if (hh) rb_atomic_add(&s.scal[S_HASH], hh);
+            }
             if (tap) {
               RB_FOR_THREADS(tid, NT) {
                 for (uint32_t i = tid; i < nt; i += NT) {
@@ -477,6 +487,7 @@ RB_HD void kpm_block(const RbKpmParams& p, uint32_t pair, uint32_t region, uint3
       v.use_all = use_all ? 1u : 0u;
       v.n_prev = n_prev; v.n_curr = n_curr; v.w2_prev = w2_prev; v.w2_curr = w2_curr;
       v.nbins = nbins;
+      v.hist_hash = s.scal[S_HASH];
       v.nticket = nbins < rv ? nbins : rv;
       for (uint32_t k = 0; k < 4; ++k) {
         RbBin b; b.dx = 0; b.dy = 0; b.cnt = 0;

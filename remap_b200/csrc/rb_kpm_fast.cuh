@@ -54,6 +54,7 @@ struct RbKpmFastParams {
   uint32_t box_x, box_y;   // TMA box: bytes per tile row, rows per box
   uint32_t nbox_y;         // boxes stacked vertically per tile (tile rows = nbox_y * box_y)
   uint32_t dybits, offbits;  // offset id = (dx + W) << dybits | (dy + H), offbits bits in all
+  uint32_t bias_x, bias_y;   // rb_kpm_big_kernel only: offset id = (dx + bias_x) << dybits | (dy + bias_y)
   const uint2* items;      // nullptr: work item i = (region i % nreg, run i / nreg).  Otherwise a second pass
   const uint32_t* nitems;  //   over (pair, region) entries another launch deferred: item i = items[i], one pair each
   uint32_t* work_counter;  // [0] work items, [2] error word; zeroed before launch
@@ -266,15 +267,18 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
       warp_top3(t0, t1, t2, g0, g1, g2);
       const uint32_t c0 = g0 >> p.offbits, c1 = g1 >> p.offbits, c2 = g2 >> p.offbits;
       uint32_t e01 = 0, e2 = 0;  // bins tied with ticket 0 / 1 (16 bits each) and 2
+      uint32_t hh = 0;           // digest of the histogram (rb_bin_hash summed over the bins)
       for (uint32_t j = lane; j < nt; j += 32) {
         const uint32_t sl = touched[j];
-        const uint32_t c = otab[sl] & cntmask;
+        const uint32_t v = otab[sl], c = v & cntmask, oid = v >> cntbits;
         e01 += (c == c0 ? 1u : 0u) + (c == c1 ? 0x10000u : 0u);
         e2 += c == c2;
+        hh += rb_bin_hash((int32_t)(oid >> p.dybits) - (int32_t)g.W, (int32_t)(oid & ((1u << p.dybits) - 1u)) - (int32_t)g.H, c);
         otab[sl] = EMPTY;
       }
       e01 = __reduce_add_sync(0xffffffffu, e01);
       e2 = __reduce_add_sync(0xffffffffu, e2);
+      hh = __reduce_add_sync(0xffffffffu, hh);
       if (lane == 0) {
         const uint32_t rv = g.region_votes;
         const uint2 cp = __ldg(p.counts + (uint64_t)(fa + t - 1) * g.nreg + region);
@@ -284,6 +288,7 @@ __global__ void __launch_bounds__(RB_FAST_NT, 2) rb_kpm_fast_kernel(const __grid
         vt.use_all = (w & PLAN_USE_ALL) ? 1u : 0u;
         vt.n_prev = cp.x; vt.n_curr = cc.x; vt.w2_prev = cp.y; vt.w2_curr = cc.y;
         vt.nbins = nt;
+        vt.hist_hash = hh;
         vt.nticket = nt < rv ? nt : rv;
         const uint32_t gk[3] = {g0, g1, g2}, ck[3] = {c0, c1, c2};
         // bins with a larger / larger-or-equal count than ticket k (counts are sorted c0 >= c1 >= c2)

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.rb_abi_version() == 3
+    assert lib.rb_abi_version() == 4
 
 
 def test_default_config_is_the_reference_constants():
@@ -62,13 +62,13 @@ def test_host_side_nibble_packing_for_the_pcie_copy():
     lib = _lib.load()
     fn = lib.rb_hostpack_frames
     fn.restype = None
-    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_uint32]
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_uint32, C.c_int]
     rng = np.random.default_rng(5)
     for W, H, n in ((320, 224, 3), (323, 227, 2), (33, 9, 5), (8, 8, 1), (1, 4, 2)):
         frames = rng.integers(0, 256, size=(n, H, W), dtype=np.uint8)
         pitch4 = ((W + 1) // 2 + 15) // 16 * 16
         out = np.full((n, H, pitch4), 0xAB, np.uint8)
-        fn(frames.ctypes.data_as(C.c_void_p), W, H, n, out.ctypes.data_as(C.c_void_p), pitch4)
+        fn(frames.ctypes.data_as(C.c_void_p), W, H, n, out.ctypes.data_as(C.c_void_p), pitch4, 3)
         lo = frames & 15
         padded = np.zeros((n, H, 2 * pitch4), np.uint8)
         padded[:, :, :W] = lo

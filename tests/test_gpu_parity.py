@@ -83,6 +83,8 @@ MATCHER_MODES = {
     "tiny_cap": dict(list_cap=64),
     "run3": dict(run_pairs=3),
     "overlap3": dict(overlap_batches=3),
+    "big_first": dict(kpm_mode=2),            # the large-region kernel (rb_kpm_big.cuh) as the first pass
+    "big_second": dict(list_cap=128),         # ... and as the second pass behind a small first-pass capacity
 }
 
 
@@ -110,6 +112,30 @@ def test_pipelined_matcher_equals_general_kernel_ballot_for_ballot():
     # scene cuts make thousands of spurious offsets in a region: those few pairs overflow the offset table
     assert outs[0][2] < 40, "the pipelined matcher should defer next to nothing on a scrolling workload"
     assert outs[2][2] > 0, "list_cap=256 should exercise the deferral path"
+    for off, ballots, _ in outs[1:]:
+        assert np.array_equal(off, outs[0][0])
+        for fld in ballots.dtype.names:
+            assert np.array_equal(ballots[fld], outs[0][1][fld]), fld
+
+
+@pytest.mark.parametrize("size,speckle,vmax", [((640, 480), 0.10, (48, 48)), ((640, 480), 0.30, (20, 20)), ((512, 384), 0.10, (30, 30))])
+def test_large_region_matcher_equals_general_kernel(size, speckle, vmax):
+    """640x480-class frames: 4-5 k keypoints per region go through rb_kpm_big_kernel; every field of every ballot
+    (histogram digest included) and every declared offset must equal the general kernel's, and nothing may be
+    deferred at the density of BASELINE configs[3]."""
+    n = 48
+    W, H = size
+    seq = synth.scrolling_tilemap(n, W, H, seed=404, speckle=speckle, vmax=vmax, cut_every=19)
+    outs = []
+    for kw in (dict(), dict(kpm_mode=1), dict(run_pairs=5)):
+        with remap_b200.Registrar(W, H, max_frames=n, **kw) as reg:
+            reg.upload(seq.frames)
+            off, _ = reg.register(n)
+            ballots = np.stack([reg.region_ballots(i) for i in range(n - 1)])
+            outs.append((off.copy(), ballots, reg.deferred_count))
+    if speckle <= 0.10:
+        assert outs[0][2] <= 16, f"large-region matcher deferred {outs[0][2]} ballots"
+    assert int(outs[0][1]["n_curr"].max()) > 2047, "the case should exceed the first-pass kernel's lists"
     for off, ballots, _ in outs[1:]:
         assert np.array_equal(off, outs[0][0])
         for fld in ballots.dtype.names:
@@ -144,6 +170,56 @@ def test_pipelined_host_registration_equals_upload_then_register(chunk, size):
     assert np.array_equal(off_a, off_b) and np.array_equal(med_a, med_b)
     for fld in ballots_a.dtype.names:
         assert np.array_equal(ballots_a[fld], ballots_b[fld]), fld
+
+
+@pytest.mark.parametrize("lane", ["raw", "packed", "auto"])
+def test_host_registration_lanes_from_pinned_memory(lane, monkeypatch):
+    """Page-locked host frames may travel raw (one copy, packed on the device) or packed by host threads, chunk by
+    chunk (rb_register_host_async picks from measured rates; RB_HOST_LANE forces one): same results either way."""
+    import torch
+    n, W, H = 300, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=92, cut_every=70)
+    pinned = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[...] = seq.frames
+    with remap_b200.Registrar(W, H, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off_a, med_a = reg.register(n, want_medians=True)
+    if lane != "auto":
+        monkeypatch.setenv("RB_HOST_LANE", lane)
+    with remap_b200.Registrar(W, H, max_frames=n, upload_chunk=32) as reg:
+        for _ in range(2):  # the second call runs on the rates measured by the first
+            reg.register_host_async(pinned.numpy())
+            off_b = reg.fetch_offsets(n - 1)
+        med_b = reg.fetch_medians(n)
+        st = reg.host_lane_stats
+    assert np.array_equal(off_a, off_b) and np.array_equal(med_a, med_b)
+    assert st["raw_chunks"] + st["packed_chunks"] == (n + 31) // 32
+    if lane == "raw":
+        assert st["packed_chunks"] == 0
+    if lane == "packed":
+        assert st["raw_chunks"] == 0
+
+
+@pytest.mark.parametrize("size,pad", [((320, 224), 0), ((323, 227), 0), ((200, 136), 12)])
+def test_registration_of_caller_packed_frames(size, pad):
+    """rb_register_host_packed4: the caller already holds 4 bit/pixel rows (any row pitch >= ceil(W / 2))."""
+    n = 90
+    W, H = size
+    seq = synth.scrolling_tilemap(n, W, H, seed=93)
+    rb = (W + 1) // 2 + pad
+    lo = np.zeros((n, H, 2 * rb), np.uint8)
+    lo[:, :, :W] = seq.frames
+    packed = (lo[:, :, 0::2] | (lo[:, :, 1::2] << 4)).astype(np.uint8)
+    if pad:
+        packed[:, :, (W + 1) // 2:] = 0xEE  # bytes beyond the row are the caller's and must be ignored
+    with remap_b200.Registrar(W, H, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off_a, med_a = reg.register(n, want_medians=True)
+    with remap_b200.Registrar(W, H, max_frames=n, upload_chunk=25) as reg:
+        reg.register_host_packed4(packed)
+        off_b = reg.fetch_offsets(n - 1)
+        med_b = reg.fetch_medians(n)
+    assert np.array_equal(off_a, off_b) and np.array_equal(med_a, med_b)
 
 
 def test_single_frame_and_two_frame_registrations():
