@@ -153,6 +153,21 @@ int rb_register(rb_ctx* ctx, size_t first, size_t n, rb_offset* out, uint8_t* ou
 int rb_keypoints(rb_ctx* ctx, size_t frame, rb_keypoint* out, size_t cap, size_t* count);
 int rb_region_ballots(rb_ctx* ctx, size_t pair, rb_region_vote* out /* grid_w*grid_h entries */);
 int rb_region_votes(rb_ctx* ctx, size_t pair, uint32_t region, rb_bin* out, size_t cap, size_t* count);
+/* Bulk parity taps for full-sequence comparisons: the ballots of pairs [pair, pair + n_pairs) of the last
+ * registration (n_pairs * grid_w * grid_h records), and per-frame digests of kpe's outputs:
+ *   splitmix(z): z += 0x9E3779B97F4A7C15; z = (z ^ z >> 30) * 0xBF58476D1CE4E5B9; z = (z ^ z >> 27) * 0x94D049BB133111EB; z ^ z >> 31
+ *   median_hash = sum over pixels with value v != 0 at index i = y * W + x of splitmix(i << 8 | v)
+ *   kp_hash     = sum over every insertion (region r, point (x, y), 13-byte code) into the grid (src/kpe.hpp:225-229,301-303)
+ *                 of splitmix((x | y << 16 | r << 32) ^ splitmix(code[0..7] ^ splitmix(code[8..12])))    (little-endian)
+ * Together with rb_region_vote.hist_hash they let a test compare EVERY frame and pair of a long sequence with the
+ * reference (oracle/_ref/ref_harness digest) without moving images or keypoint lists. */
+typedef struct rb_frame_digest {
+  uint64_t median_hash, kp_hash;
+  uint32_t keypoints;   /* unique pixels                        */
+  uint32_t insertions;  /* sum over regions (overlaps count twice or four times) */
+} rb_frame_digest;
+int rb_frame_digests(rb_ctx* ctx, size_t first, size_t n, rb_frame_digest* out);
+int rb_fetch_ballots(rb_ctx* ctx, size_t pair, size_t n_pairs, rb_region_vote* out);
 
 /* fde::details::generate_mask (src/fde.hpp:19-55): mask[y][x] = 0xFF where the background map
  * equals the frame placed at (px, py), else 0.  bg = bgH*bgW bytes, frame/out_mask = H*W bytes. */

@@ -20,6 +20,14 @@
 //                                           the filtered fragments' dots; R > 1 repeats fdf::filter for timing
 //   heat  <frames.bin> W H N <out.bin>      aws::details::compare (src/aws.hpp:37-60) over every consecutive pair,
 //                                           from aws::scan's initial heat map of ones; dumps the map after each pair
+//   digest <frames.bin> W H N <out.bin> T [C]  FULL-SEQUENCE parity record, T host threads on contiguous shards (one-frame
+//                                           overlap).  Per frame: order-independent 64-bit digests of the median image
+//                                           and of every (region, point, code) insertion of the grid; per pair: the
+//                                           reference's kpm::match result and, per region, the weight switch, the
+//                                           number of bins, a digest of the whole offset histogram and the ticket in
+//                                           the REFERENCE'S OWN order (top_offsets over libstdc++'s unordered_map).
+//                                           C = 1 adds (fragment, x, y) of every frame from the unmodified
+//                                           frc::collector run on the same shards (stitched at the shard borders).
 //   splice <frames.bin> W H N <out.bin>     frc::collector::collect + complete, then (a) every fragment as a
 //                                           fgs snippet (blend, kpe with a 1x1 grid, src/fgs.hpp:80-89) and the
 //                                           cellular kpm::match (src/kpm.hpp:371-393) of every snippet pair with
@@ -312,6 +320,192 @@ int run_bench(int argc, char** argv) {
   return 0;
 }
 
+
+// ---- digest -----------------------------------------------------------------------------
+// Record layouts (mirrored by tests/digest_check.py and, for the digests themselves, by rb_digest_kernel):
+//   splitmix(z): z += 0x9E3779B97F4A7C15; z = (z ^ z >> 30) * 0xBF58476D1CE4E5B9; z = (z ^ z >> 27) * 0x94D049BB133111EB; z ^ z >> 31
+//   median_hash = sum over pixels with value v != 0 at index i = y * W + x of splitmix(i << 8 | v)
+//   kp_hash     = sum over regions r and insertions (code, (x, y)) of
+//                 splitmix((x | y << 16 | r << 32) ^ splitmix(code[0..7] ^ splitmix(code[8..12])))   (little-endian words)
+//   hist_hash   = 32-bit sum over the bins of a region's totalizator_t of the bin digest of include/remap_b200.h
+static inline std::uint64_t splitmix(std::uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static inline std::uint32_t bin_hash(std::int32_t dx, std::int32_t dy, std::uint32_t cnt) {
+  std::uint32_t h = (static_cast<std::uint32_t>(dx) & 0xFFFFu) | (static_cast<std::uint32_t>(dy) << 16);
+  h = h * 0x9E3779B1u ^ cnt * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+
+#pragma pack(push, 1)
+struct frame_digest { std::uint64_t median_hash, kp_hash; std::uint32_t insertions; std::uint32_t n[8], w2[8]; };
+struct region_digest { std::uint32_t use_all, nbins, hist_hash, nticket; std::int32_t tdx[3], tdy[3]; std::uint32_t tcnt[3]; };
+struct pair_digest { std::uint32_t valid; std::int32_t dx, dy; std::uint32_t active; region_digest r[8]; };
+#pragma pack(pop)
+
+template<typename Image>
+frame_digest digest_frame(Image const& median, frc::grid_type const& grid, std::size_t W, std::size_t H) {
+  frame_digest d{};
+  auto const* m = reinterpret_cast<std::uint8_t const*>(median.data());
+  for (std::size_t i = 0; i < W * H; ++i)
+    if (m[i]) d.median_hash += splitmix((static_cast<std::uint64_t>(i) << 8) | m[i]);
+  std::size_t r = 0;
+  for (auto& region : grid.regions()) {
+    for (auto& [code, pts] : region.points()) {
+      std::uint64_t lo = 0, hi = 0;
+      std::memcpy(&lo, code.data(), 8);
+      std::memcpy(&hi, reinterpret_cast<std::uint8_t const*>(code.data()) + 8, 5);
+      std::uint64_t const ch = splitmix(lo ^ splitmix(hi));
+      for (auto& p : pts) {
+        std::uint64_t const a = static_cast<std::uint64_t>(p.x_) | (static_cast<std::uint64_t>(p.y_) << 16) |
+                                (static_cast<std::uint64_t>(r) << 32);
+        d.kp_hash += splitmix(a ^ ch);
+        ++d.insertions;
+      }
+    }
+    if (r < 8) {
+      d.n[r] = static_cast<std::uint32_t>(region.counts()[1] + region.counts()[2]);
+      d.w2[r] = static_cast<std::uint32_t>(region.counts()[2]);
+    }
+    ++r;
+  }
+  return d;
+}
+
+template<typename Alloc>
+pair_digest digest_pair(frc::grid_type const& prev, frc::grid_type const& curr, Alloc const& alloc) {
+  pair_digest d{};
+  match_config cfg{alloc};
+  auto off = kpm::match(cfg, prev, curr);  // the reference's own declaration
+  d.valid = off ? 1u : 0u;
+  d.dx = off ? off->x_ : 0;
+  d.dy = off ? off->y_ : 0;
+  d.active = static_cast<std::uint32_t>(kpm::details::get_active(curr));
+  auto pregs{prev.regions()}, cregs{curr.regions()};
+  for (std::size_t i = 0; i < frc::grid_type::region_count && i < 8; ++i) {
+    bool use_all = pregs[i].counts()[2] < match_config::weight_switch || cregs[i].counts()[2] <= match_config::weight_switch;
+    auto total = use_all ? kpm::details::count_offsets<true>(cfg, pregs[i], cregs[i])
+                         : kpm::details::count_offsets<false>(cfg, pregs[i], cregs[i]);
+    auto& rd = d.r[i];
+    rd.use_all = use_all ? 1u : 0u;
+    rd.nbins = static_cast<std::uint32_t>(total.size());
+    for (auto& [o, c] : total) rd.hist_hash += bin_hash(o.x_, o.y_, static_cast<std::uint32_t>(c));
+    auto ticket = kpm::details::top_offsets(cfg, total, match_config::region_votes);  // consumes `total`
+    rd.nticket = static_cast<std::uint32_t>(ticket.size());
+    std::size_t k = 0;
+    for (auto& v : ticket) {
+      if (k < 3) { rd.tdx[k] = v.offset_.x_; rd.tdy[k] = v.offset_.y_; rd.tcnt[k] = static_cast<std::uint32_t>(v.count_); }
+      ++k;
+    }
+  }
+  return d;
+}
+
+// frames [first, last) (first = own range minus the overlap frame): frame digests for all of them, pair digests for
+// pairs (i - 1, i), i in (first, last)
+void digest_shard(std::uint8_t const* frames, std::size_t W, std::size_t H, std::size_t first, std::size_t last,
+                  frame_digest* fd, pair_digest* pd) {
+  extractor_t extractor{mrl::dimensions_t{W, H}};
+  all::memory_stack<cpl::nat_cc> memory{};
+  memory_feed feed{frames, W, H, first, last};
+  auto first_alloc{memory.previous()};
+  auto frame{feed.produce(first_alloc)};
+  frc::image_type median{frame.image_.dimensions(), first_alloc};
+  auto pkeys{extractor.extract(frame.image_, median, first_alloc)};
+  fd[first] = digest_frame(median, pkeys, W, H);
+  std::size_t i = first + 1;
+  while (feed.has_more()) {
+    all::memory_swing swing{memory};
+    pixel_alloc_t alloc{swing};
+    auto fr{feed.produce(alloc)};
+    frc::image_type med{fr.image_.dimensions(), alloc};
+    auto keys{extractor.extract(fr.image_, med, alloc)};
+    fd[i] = digest_frame(med, keys, W, H);
+    pd[i - 1] = digest_pair(pkeys, keys, alloc);
+    pkeys = std::move(keys);
+    ++i;
+  }
+}
+
+// the unmodified collector on frames [first, last): (fragment, x, y) per frame relative to the shard's first frame
+void collect_shard(std::uint8_t const* frames, std::size_t W, std::size_t H, std::size_t first, std::size_t last,
+                   std::size_t own, std::int32_t* rec /* 3 per frame, indexed by global frame number; only frames >= own */) {
+  frc::collector collector{mrl::dimensions_t{W, H}};
+  memory_feed feed{frames, W, H, first, last};
+  collector.collect(feed, null_compression{},
+                    [&](fgm::fragment const& frag, frc::frame_type const& fr, frc::image_type const&, frc::grid_type const&) {
+                      auto& pos = frag.frames().back().position_;  // raw, before normalize()
+                      rec[3 * fr.number_ + 1] = pos.x_;
+                      rec[3 * fr.number_ + 2] = pos.y_;
+                    });
+  auto frags = collector.complete();
+  std::int32_t fi = 0;
+  for (auto& f : frags) {
+    for (auto& fr : f.frames())
+      if (fr.number_ >= own) rec[3 * fr.number_] = fi;  // the overlap frame belongs to the previous shard
+    ++fi;
+  }
+}
+
+int run_digest(int argc, char** argv) {
+  if (argc < 8) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  std::size_t T = std::atoll(argv[7]);
+  bool const with_collector = argc > 8 && std::atoi(argv[8]) != 0;
+  auto frames = read_file(argv[2], N * W * H);
+  if (T < 1) T = 1;
+  if (T > N / 2) T = std::max<std::size_t>(1, N / 2);
+  std::vector<frame_digest> fd(N);
+  std::vector<pair_digest> pd(N > 1 ? N - 1 : 0);
+  std::vector<std::int32_t> rec(with_collector ? 3 * N : 0, 0), loc(with_collector ? 3 * N : 0, 0);
+  std::vector<std::size_t> starts;
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    std::vector<std::thread> th;
+    for (std::size_t t = 0; t < T; ++t) {
+      std::size_t lo = t * N / T, hi = (t + 1) * N / T;
+      std::size_t first = lo == 0 ? 0 : lo - 1;
+      starts.push_back(first);
+      th.emplace_back([&, first, lo, hi] {
+        digest_shard(frames.data(), W, H, first, hi, fd.data(), pd.data());
+        if (with_collector) collect_shard(frames.data(), W, H, first, hi, lo, loc.data());
+      });
+    }
+    for (auto& x : th) x.join();
+  }
+  if (with_collector) {
+    // stitch: a shard's first frame is the previous shard's last (already global); frames of the shard's fragment 0
+    // continue that frame's fragment at its position, later fragments of the shard are new ones
+    for (std::size_t t = 0; t < T; ++t) {
+      std::size_t lo = t * N / T, hi = (t + 1) * N / T;
+      std::size_t first = starts[t];
+      std::int32_t bf = 0, bx = 0, by = 0;
+      if (t > 0) { bf = rec[3 * first]; bx = rec[3 * first + 1]; by = rec[3 * first + 2]; }
+      for (std::size_t i = (t == 0 ? 0 : lo); i < hi; ++i) {
+        std::int32_t f = loc[3 * i], x = loc[3 * i + 1], y = loc[3 * i + 2];
+        if (f == 0) { rec[3 * i] = bf; rec[3 * i + 1] = bx + x; rec[3 * i + 2] = by + y; }
+        else { rec[3 * i] = bf + f; rec[3 * i + 1] = x; rec[3 * i + 2] = y; }
+      }
+    }
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  FILE* out = std::fopen(argv[6], "wb");
+  if (!out) return 2;
+  std::fwrite("RMDG", 1, 4, out);
+  put32(out, W); put32(out, H); put32(out, N); put32(out, with_collector ? 1u : 0u);
+  std::fwrite(fd.data(), sizeof(frame_digest), fd.size(), out);
+  std::fwrite(pd.data(), sizeof(pair_digest), pd.size(), out);
+  if (with_collector) std::fwrite(rec.data(), 4, rec.size(), out);
+  std::fclose(out);
+  std::printf("{\"mode\": \"digest\", \"threads\": %zu, \"frames\": %zu, \"seconds\": %.3f}\n", T, N,
+              std::chrono::duration<double>(t1 - t0).count());
+  return 0;
+}
+
 int run_mask(int argc, char** argv) {
   if (argc < 11) return 1;
   std::size_t bw = std::atoll(argv[3]), bh = std::atoll(argv[4]);
@@ -548,6 +742,7 @@ int main(int argc, char** argv) {
   std::string mode = argv[1];
   if (mode == "dump") return run_dump(argc, argv);
   if (mode == "bench") return run_bench(argc, argv);
+  if (mode == "digest") return run_digest(argc, argv);
   if (mode == "mask") return run_mask(argc, argv);
   if (mode == "filter") return run_filter(argc, argv);
   if (mode == "splice") return run_splice(argc, argv);

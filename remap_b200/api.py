@@ -19,7 +19,8 @@ BIN_DTYPE = np.dtype([("dx", "<i4"), ("dy", "<i4"), ("cnt", "<u4")])
 VOTE_DTYPE = np.dtype([("use_all", "<u4"), ("n_prev", "<u4"), ("n_curr", "<u4"), ("w2_prev", "<u4"),
                        ("w2_curr", "<u4"), ("nbins", "<u4"), ("nticket", "<u4"),
                        ("ticket", BIN_DTYPE, (4,)), ("ngt", "<u4", (4,)), ("nge", "<u4", (4,)), ("hist_hash", "<u4")])
-assert KEYPOINT_DTYPE.itemsize == 24 and OFFSET_DTYPE.itemsize == 12
+FRAME_DIGEST_DTYPE = np.dtype([("median_hash", "<u8"), ("kp_hash", "<u8"), ("keypoints", "<u4"), ("insertions", "<u4")])
+assert KEYPOINT_DTYPE.itemsize == 24 and OFFSET_DTYPE.itemsize == 12 and VOTE_DTYPE.itemsize == 112
 
 
 class RemapError(RuntimeError):
@@ -152,6 +153,18 @@ class Registrar:
     def region_ballots(self, pair):
         out = np.zeros(self.nreg, VOTE_DTYPE)
         self._check(self._lib.rb_region_ballots(self._ctx, pair, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def fetch_ballots(self, n_pairs, pair=0):
+        """(n_pairs, nreg) VOTE_DTYPE: every region ballot of pairs [pair, pair + n_pairs) in one copy."""
+        out = np.zeros((n_pairs, self.nreg), VOTE_DTYPE)
+        self._check(self._lib.rb_fetch_ballots(self._ctx, pair, n_pairs, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def frame_digests(self, n, first=0):
+        """(n,) FRAME_DIGEST_DTYPE: digests of kpe's outputs per frame (rb_frame_digests)."""
+        out = np.zeros(n, FRAME_DIGEST_DTYPE)
+        self._check(self._lib.rb_frame_digests(self._ctx, first, n, out.ctypes.data_as(C.c_void_p)))
         return out
 
     def region_votes(self, pair, region):

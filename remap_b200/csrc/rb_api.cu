@@ -269,6 +269,79 @@ __global__ void rb_fgmask_kernel(const uint8_t* __restrict__ bg, long long idx, 
   }
 }
 
+
+// Parity tap for full-sequence comparisons (tests/digest_check.py against the compiled reference in digest mode): per frame,
+// order-independent 64-bit digests of kpe's two outputs -- the median image and every (region, point, code)
+// insertion kpe::extractor makes into the grid (src/kpe.hpp:225-229,301-303; code layout src/kpe.hpp:342-379).
+//   median_hash = sum over pixels with value v != 0 at index i = y * W + x of splitmix(i << 8 | v)
+//   kp_hash     = sum over insertions of splitmix((x | y << 16 | region << 32) ^ splitmix(code[0..7] ^ splitmix(code[8..12])))
+__device__ __forceinline__ unsigned long long rb_splitmix(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256) rb_digest_kernel(const RbGeom g, const uint8_t* __restrict__ frames, const uint8_t* __restrict__ median,
+                                                        const uint32_t* __restrict__ kpbits, const uint32_t* __restrict__ w2bits,
+                                                        uint32_t first, rb_frame_digest* __restrict__ out) {
+  const uint32_t f = first + blockIdx.x, tid = threadIdx.x, W = g.W, H = g.H;
+  unsigned long long mh = 0, kh = 0;
+  uint32_t nk = 0, ni = 0;
+  if (median) {
+    const uint8_t* m = median + (uint64_t)f * g.median_stride + 2;  // pixel x at byte x + 2 of a row
+    for (uint32_t i = tid; i < W * H; i += blockDim.x) {
+      const uint32_t y = i / W, x = i - y * W;
+      const uint32_t v = m[(uint64_t)y * g.mpitch + x];
+      if (v) mh += rb_splitmix(((unsigned long long)i << 8) | v);
+    }
+  }
+  const uint8_t* fr = frames + (uint64_t)f * g.frame_stride;
+  const uint32_t* kpf = kpbits + (uint64_t)f * H * g.NS;
+  const uint32_t* w2f = w2bits + (uint64_t)f * H * g.NS;
+  for (uint32_t wi = tid; wi < H * g.NS; wi += blockDim.x) {
+    const uint32_t y = wi / g.NS, j = wi - y * g.NS;
+    uint32_t w = kpf[wi];
+    const uint32_t w2 = w2f[wi];
+    while (w) {
+      const uint32_t b = (uint32_t)__ffs((int)w) - 1;
+      w &= w - 1;
+      const uint32_t x = RB_STRIP_OUT * j + b, weight = ((w2 >> b) & 1u) ? 2u : 1u;
+      uint8_t v[25];
+      for (int r = 0; r < 5; ++r)
+        for (int cc = 0; cc < 5; ++cc) v[5 * r + cc] = fr[(uint64_t)(y - 2 + r) * g.pitch + (x - 2 + cc)] & 15;
+      auto at = [&](int r, int cc) { return (unsigned long long)v[5 * r + cc]; };
+      auto byte = [&](int lo_r, int lo_c, int hi_r, int hi_c) { return at(lo_r, lo_c) | (at(hi_r, hi_c) << 4); };
+      const unsigned long long lo = byte(0, 0, 0, 1) | (byte(0, 2, 0, 3) << 8) | (byte(1, 0, 0, 4) << 16) | (byte(1, 1, 1, 2) << 24) |
+                                    (byte(1, 3, 1, 4) << 32) | (byte(2, 0, 2, 1) << 40) | (byte(2, 2, 2, 3) << 48) | (byte(3, 0, 2, 4) << 56);
+      const unsigned long long hi = byte(3, 1, 3, 2) | (byte(3, 3, 3, 4) << 8) | (byte(4, 0, 4, 1) << 16) | (byte(4, 2, 4, 3) << 24) |
+                                    (((unsigned long long)weight | (at(4, 4) << 4)) << 32);
+      const unsigned long long ch = rb_splitmix(lo ^ rb_splitmix(hi));
+      ++nk;
+      for (uint32_t a = 0; a < g.grid_w; ++a)
+        if (x >= g.col0[a] && x < g.col1[a])
+          for (uint32_t bb = 0; bb < g.grid_h; ++bb)
+            if (y >= g.row0[bb] && y < g.row1[bb]) {
+              const unsigned long long r = g.grid_h * a + bb;  // src/kpr.hpp:71-74
+              kh += rb_splitmix(((unsigned long long)x | ((unsigned long long)y << 16) | (r << 32)) ^ ch);
+              ++ni;
+            }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mh += __shfl_down_sync(0xffffffffu, mh, o);
+    kh += __shfl_down_sync(0xffffffffu, kh, o);
+    nk += __shfl_down_sync(0xffffffffu, nk, o);
+    ni += __shfl_down_sync(0xffffffffu, ni, o);
+  }
+  if ((tid & 31) == 0) {
+    rb_frame_digest* d = out + blockIdx.x;
+    if (mh) atomicAdd(reinterpret_cast<unsigned long long*>(&d->median_hash), mh);
+    if (kh) atomicAdd(reinterpret_cast<unsigned long long*>(&d->kp_hash), kh);
+    if (nk) atomicAdd(&d->keypoints, nk);
+    if (ni) atomicAdd(&d->insertions, ni);
+  }
+}
+
 // popcount of K1's keypoint bit maps (statistics for the roofline's K term)
 __global__ void rb_count_kernel(const uint32_t* __restrict__ bits, size_t nwords, unsigned long long* total) {
   unsigned long long loc = 0;
@@ -1334,6 +1407,41 @@ int rb_region_ballots(rb_ctx* c, size_t pair, rb_region_vote* out) {
   RB_CUDA(c, cudaSetDevice(c->device));
   RB_CUDA(c, cudaMemcpyAsync(out, c->d_votes + (c->reg_first + pair) * c->g.nreg, c->g.nreg * sizeof(RbRegionVote),
                              cudaMemcpyDeviceToHost, c->stream));
+  RB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RB_OK;
+}
+
+
+int rb_frame_digests(rb_ctx* c, size_t first, size_t n, rb_frame_digest* out) {
+  if (!c || (!out && n)) return RB_ERR_INVALID;
+  if (first + n > c->uploaded || first < c->med_lo || first + n > c->med_hi) {
+    c->err = "rb_frame_digests: frames not registered";
+    return RB_ERR_STATE;
+  }
+  if (n == 0) return RB_OK;
+  RB_CUDA(c, cudaSetDevice(c->device));
+  rb_frame_digest* d = nullptr;
+  RB_CUDA(c, cudaMalloc(&d, n * sizeof(rb_frame_digest)));
+  cudaError_t e = cudaMemsetAsync(d, 0, n * sizeof(rb_frame_digest), c->stream);
+  if (e == cudaSuccess) {
+    rb_digest_kernel<<<(uint32_t)n, 256, 0, c->stream>>>(c->g, c->d_frames, c->d_median, c->d_kp, c->d_w2, (uint32_t)first, d);
+    ++c->launches;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, n * sizeof(rb_frame_digest), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) { c->err = std::string("rb_frame_digests: ") + cudaGetErrorString(e); return RB_ERR_CUDA; }
+  return RB_OK;
+}
+
+int rb_fetch_ballots(rb_ctx* c, size_t pair, size_t n_pairs, rb_region_vote* out) {
+  if (!c || (!out && n_pairs)) return RB_ERR_INVALID;
+  if (c->reg_n < 2 || pair + n_pairs > c->reg_n - 1) { c->err = "rb_fetch_ballots: pairs not registered"; return RB_ERR_STATE; }
+  RB_CUDA(c, cudaSetDevice(c->device));
+  if (n_pairs)
+    RB_CUDA(c, cudaMemcpyAsync(out, c->d_votes + (c->reg_first + pair) * c->g.nreg, n_pairs * c->g.nreg * sizeof(RbRegionVote),
+                               cudaMemcpyDeviceToHost, c->stream));
   RB_CUDA(c, cudaStreamSynchronize(c->stream));
   return RB_OK;
 }
