@@ -133,7 +133,7 @@ int rb_register_host_async(rb_ctx* ctx, const uint8_t* frames, size_t first, siz
  * to 4 bit/pixel (half the bytes cross PCIe), or -- page-locked `frames` only -- the chunk is copied as it is and
  * packed on the device; both lanes work at the same time.  rb_host_lane_stats reports the last call's split. */
 int rb_host_lane_stats(rb_ctx* ctx, uint64_t* raw_chunks, uint64_t* packed_chunks, double* link_GBps, double* pack_fps,
-                       int* threads);
+                       int* threads, uint64_t* h2d_bytes);
 /* The same for a caller that already holds 4 bit/pixel frames (the layout a packed capture would have: pixel x in
  * nibble x & 1 of byte x >> 1; rows of row_bytes >= ceil(W / 2) bytes, frames back to back): one copy per chunk,
  * no host work. */
@@ -303,6 +303,7 @@ uint64_t rb_kernel_launches(rb_ctx* ctx);              /* kernels launched by th
 int rb_deferred_count(rb_ctx* ctx, uint32_t* count);
 size_t rb_device_bytes(rb_ctx* ctx);                   /* HBM held by this context                  */
 const char* rb_last_error(rb_ctx* ctx);
+const char* rb_matcher_kernel(rb_ctx* ctx);           /* the kernel that takes the regions first (introspection) */
 uint32_t rb_abi_version(void);
 
 #ifdef __cplusplus

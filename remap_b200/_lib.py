@@ -25,7 +25,7 @@ SYMBOLS = [
     "rb_count_keypoints", "rb_alloc_host", "rb_free_host", "rb_deferred_count", "rb_register_host_async", "rb_blit_blend",
     "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
     "rb_aws_compare", "rb_map_device", "rb_blend_map", "rb_map_export", "rb_blend_map_peers", "rb_sum_map_slice", "rb_blend_map_slices", "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
-    "rb_host_lane_stats", "rb_register_host_packed4", "rb_frame_digests", "rb_fetch_ballots",
+    "rb_host_lane_stats", "rb_register_host_packed4", "rb_frame_digests", "rb_fetch_ballots", "rb_matcher_kernel",
 ]
 
 
@@ -77,7 +77,7 @@ def load(build_if_missing: bool = False):
     lib.rb_register_host_packed4.argtypes = [vp, vp, sz, sz, sz]
     lib.rb_host_lane_stats.restype = C.c_int
     lib.rb_host_lane_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
-                                       C.POINTER(C.c_double), C.POINTER(C.c_int)]
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     lib.rb_frame_digests.restype = C.c_int
     lib.rb_frame_digests.argtypes = [vp, sz, sz, vp]
     lib.rb_fetch_ballots.restype = C.c_int
@@ -142,6 +142,8 @@ def load(build_if_missing: bool = False):
     lib.rb_device_bytes.argtypes = [vp]
     lib.rb_last_error.restype = C.c_char_p
     lib.rb_last_error.argtypes = [vp]
+    lib.rb_matcher_kernel.restype = C.c_char_p
+    lib.rb_matcher_kernel.argtypes = [vp]
     lib.rb_offsets_device.restype = vp
     lib.rb_offsets_device.argtypes = [vp]
     lib.rb_count_keypoints.restype = C.c_int

@@ -116,11 +116,17 @@ class Registrar:
         self._keep = packed
 
     @property
+    def matcher_kernel(self) -> str:
+        return self._lib.rb_matcher_kernel(self._ctx).decode()
+
+    @property
     def host_lane_stats(self):
         """Last register_host_async: chunks sent raw / packed, and the measured rates behind the choice."""
-        raw, pk, link, fps, th = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_double(), C.c_int()
-        self._check(self._lib.rb_host_lane_stats(self._ctx, C.byref(raw), C.byref(pk), C.byref(link), C.byref(fps), C.byref(th)))
-        return dict(raw_chunks=raw.value, packed_chunks=pk.value, link_GBps=link.value, pack_fps=fps.value, threads=th.value)
+        raw, pk, link, fps, th, nb = C.c_uint64(), C.c_uint64(), C.c_double(), C.c_double(), C.c_int(), C.c_uint64()
+        self._check(self._lib.rb_host_lane_stats(self._ctx, C.byref(raw), C.byref(pk), C.byref(link), C.byref(fps), C.byref(th),
+                                                 C.byref(nb)))
+        return dict(raw_chunks=raw.value, packed_chunks=pk.value, link_GBps=link.value, pack_fps=fps.value, threads=th.value,
+                    h2d_bytes=nb.value)
 
     def fetch_offsets(self, n_pairs, out=None):
         if out is None:

@@ -450,6 +450,7 @@ struct rb_ctx {
   double link_Bps;         // estimated host -> device rate of this context's link (bytes / s)
   double pack_fps;         // estimated rate of the host packer (frames / s)
   uint64_t lane_raw, lane_packed;  // chunks of the last rb_register_host_async call that went raw / packed
+  uint64_t lane_bytes;             // bytes that call put on the link
   int host_threads;        // packer threads of this context
   size_t stage_frames;
   uint64_t launches;
@@ -791,6 +792,10 @@ void rb_destroy(rb_ctx* c) {
 }
 
 const char* rb_last_error(rb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+const char* rb_matcher_kernel(rb_ctx* c) {
+  if (!c) return "";
+  return c->cfg.kpm_mode == 1 ? "rb_kpm_kernel" : c->big_primary ? "rb_kpm_big_kernel" : "rb_kpm_fast_kernel";
+}
 const rb_offset* rb_offsets_device(rb_ctx* c) { return c ? c->d_offsets + c->reg_first : nullptr; }
 
 int rb_count_keypoints(rb_ctx* c, size_t first, size_t n, uint64_t* total) {
@@ -1212,6 +1217,7 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   RB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0));
   if (c->d_work) RB_CUDA(c, cudaMemsetAsync(c->d_work, 0, 16, c->stream));
   c->lane_raw = c->lane_packed = 0;
+  c->lane_bytes = 0;
   const double raw_bytes_pf = (double)g.W * g.H, packed_bytes_pf = (double)c->frame_stride4;
   size_t oldest = 0;          // first chunk whose copy may still be in flight
   double inflight_bytes = 0;  // bytes queued on the link and not yet known to have landed
@@ -1270,6 +1276,7 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
     }
     RB_CUDA(c, cudaEventRecord(landed, c->copy_stream));
     inflight_bytes += chunk_bytes[k];
+    c->lane_bytes += (uint64_t)chunk_bytes[k];
     rc = chunk_landed(c, first, at, m, !raw, landed);
     if (rc != RB_OK) return rc;
   }
@@ -1311,13 +1318,15 @@ int rb_register_host_packed4(rb_ctx* c, const uint8_t* packed, size_t row_bytes,
 }
 
 // Last rb_register_host_async: chunks that went raw / packed, and the rate estimates the choice was made from.
-int rb_host_lane_stats(rb_ctx* c, uint64_t* raw_chunks, uint64_t* packed_chunks, double* link_GBps, double* pack_fps, int* threads) {
+int rb_host_lane_stats(rb_ctx* c, uint64_t* raw_chunks, uint64_t* packed_chunks, double* link_GBps, double* pack_fps, int* threads,
+                       uint64_t* h2d_bytes) {
   if (!c) return RB_ERR_INVALID;
   if (raw_chunks) *raw_chunks = c->lane_raw;
   if (packed_chunks) *packed_chunks = c->lane_packed;
   if (link_GBps) *link_GBps = c->link_Bps / 1e9;
   if (pack_fps) *pack_fps = c->pack_fps;
   if (threads) *threads = packer_threads(c);
+  if (h2d_bytes) *h2d_bytes = c->lane_bytes;
   return RB_OK;
 }
 

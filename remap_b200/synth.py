@@ -100,10 +100,94 @@ def render(world: np.ndarray, path: np.ndarray, w: int, h: int) -> np.ndarray:
     return out
 
 
+class TilemapPlan:
+    """Everything about a scrolling_tilemap sequence except the pixels: worlds, camera path, levels, sprite set.
+    render(a, b) draws frames [a, b); building the plan once lets a long sequence be rendered batch by batch
+    (tools/run_config.py) with the very same result as one scrolling_tilemap call."""
+
+    def __init__(self, n: int, w: int = 320, h: int = 224, seed: int = 1, *, world_w: int = 4096, world_h: int = 2048,
+                 n_tiles: int = 64, speckle: float = 0.05, vmax=(4, 3), sprites: int = 0, cut_every: int = 0,
+                 levels: int = 1, parallax: int = 0, detail: int = 1, sprite_motion: str = "stateful"):
+        rng = np.random.default_rng(seed)
+        self.n, self.w, self.h = n, w, h
+        world_w = max(world_w, w + 64)
+        world_h = max(world_h, h + 64)
+        self.worlds = [make_world(rng, world_w, world_h, n_tiles, speckle, detail) for _ in range(max(1, levels))]
+        path = camera_path(rng, n, w, h, world_w, world_h, vmax)
+        level = np.zeros(n, np.int32)
+        if cut_every > 0:
+            i = int(rng.integers(cut_every // 2 + 1, cut_every * 3 // 2 + 2))
+            cur = 0
+            while i < n:
+                cur = (cur + 1) % len(self.worlds) if len(self.worlds) > 1 else cur
+                jump = np.array([int(rng.integers(0, world_w - w + 1)), int(rng.integers(0, world_h - h + 1))])
+                delta = jump - path[i]
+                path[i:] += delta                                   # teleport, keep the velocity plan
+                np.clip(path[i:, 0], 0, world_w - w, out=path[i:, 0])
+                np.clip(path[i:, 1], 0, world_h - h, out=path[i:, 1])
+                level[i:] = cur
+                i += int(rng.integers(cut_every // 2 + 1, cut_every * 3 // 2 + 2))
+        self.path, self.level = path, level
+        self.parallax = parallax
+        self.far = make_world(rng, world_w, world_h, n_tiles, speckle, detail) if parallax > 0 else None
+        self.sprites, self.sprite_motion = sprites, sprite_motion
+        if sprites > 0:
+            self.sw = rng.integers(12, 25, size=sprites)
+            self.sh = rng.integers(12, 25, size=sprites)
+            self.tex = [rng.integers(0, 16, size=(int(self.sh[k]), int(self.sw[k])), dtype=np.uint8) for k in range(sprites)]
+            self.pos0 = np.stack([rng.integers(0, w - 24, size=sprites), rng.integers(0, h - 24, size=sprites)], 1).astype(np.float64)
+            self.vel0 = rng.uniform(-3, 3, size=(sprites, 2))
+        self.meta = dict(n=n, w=w, h=h, seed=seed, n_tiles=n_tiles, speckle=speckle, vmax=tuple(vmax), sprites=sprites,
+                         cut_every=cut_every, levels=levels, parallax=parallax, detail=detail, sprite_motion=sprite_motion)
+
+    def render(self, a: int = 0, b: int | None = None, out: np.ndarray | None = None) -> Sequence:
+        b = self.n if b is None else b
+        n, w, h = b - a, self.w, self.h
+        assert self.sprites == 0 or self.sprite_motion == "closed" or a == 0, \
+            "stateful sprites need the sequence rendered from frame 0; use sprite_motion='closed'"
+        path, level = self.path[a:b].copy(), self.level[a:b].copy()
+        frames = out if out is not None else np.empty((n, h, w), np.uint8)
+        assert frames.shape == (n, h, w) and frames.dtype == np.uint8
+        for i in range(n):
+            x, y = int(path[i, 0]), int(path[i, 1])
+            frames[i] = self.worlds[level[i]][y:y + h, x:x + w]
+        if self.parallax > 0:
+            band = (np.arange(h) // self.parallax) % 2 == 1
+            for i in range(n):
+                x, y = int(path[i, 0]) // 2, int(path[i, 1]) // 2
+                frames[i][band] = self.far[y:y + h, x:x + w][band]
+        if self.sprites > 0:
+            sw, sh, tex, sprites = self.sw, self.sh, self.tex, self.sprites
+            if self.sprite_motion == "closed":
+                span = np.stack([w - sw, h - sh], 1).astype(np.float64)          # a sprite stays inside the frame
+                for i in range(n):
+                    p = self.pos0 + self.vel0 * float(a + i)
+                    m = np.mod(p, 2 * span)
+                    p = np.where(m > span, 2 * span - m, m)
+                    for k in range(sprites):
+                        px, py = int(p[k, 0]), int(p[k, 1])
+                        frames[i, py:py + int(sh[k]), px:px + int(sw[k])] = tex[k][:h - py, :w - px]
+            else:
+                pos, vel = self.pos0.copy(), self.vel0.copy()
+                for i in range(n):
+                    for k in range(sprites):
+                        px, py = int(pos[k, 0]), int(pos[k, 1])
+                        frames[i, py:py + int(sh[k]), px:px + int(sw[k])] = tex[k][:h - py, :w - px]
+                    pos += vel
+                    for k in range(sprites):
+                        if pos[k, 0] < 0 or pos[k, 0] > w - sw[k]:
+                            vel[k, 0] = -vel[k, 0]
+                            pos[k, 0] = min(max(pos[k, 0], 0), w - sw[k])
+                        if pos[k, 1] < 0 or pos[k, 1] > h - sh[k]:
+                            vel[k, 1] = -vel[k, 1]
+                            pos[k, 1] = min(max(pos[k, 1], 0), h - sh[k])
+        return Sequence(frames=frames, path=path, level=level, meta=dict(self.meta, n=n))
+
+
 def scrolling_tilemap(n: int, w: int = 320, h: int = 224, seed: int = 1, *, world_w: int = 4096,
                       world_h: int = 2048, n_tiles: int = 64, speckle: float = 0.05,
                       vmax=(4, 3), sprites: int = 0, cut_every: int = 0, levels: int = 1,
-                      parallax: int = 0, detail: int = 1, frame_range=None) -> Sequence:
+                      parallax: int = 0, detail: int = 1, frame_range=None, sprite_motion: str = "stateful") -> Sequence:
     """The workload family of BASELINE.json ``configs``.
 
     sprites    number of moving textured rectangles drawn over the background (config 3)
@@ -112,61 +196,15 @@ def scrolling_tilemap(n: int, w: int = 320, h: int = 224, seed: int = 1, *, worl
     parallax   band height in pixels of a second layer scrolling at half speed; 0 = none
     frame_range (a, b): render only frames [a, b) of the n-frame sequence (a rank's shard); path and
                level still describe the rendered frames only
+    sprite_motion "stateful": sprites bounce step by step (needs the whole sequence rendered in order);
+               "closed": a sprite's position is a closed-form triangle wave of the frame index, so any frame_range of a
+               long sequence can be rendered on its own (multi-GPU shards of config 3)
     """
-    rng = np.random.default_rng(seed)
-    world_w = max(world_w, w + 64)
-    world_h = max(world_h, h + 64)
-    worlds = [make_world(rng, world_w, world_h, n_tiles, speckle, detail) for _ in range(max(1, levels))]
-    path = camera_path(rng, n, w, h, world_w, world_h, vmax)
-    level = np.zeros(n, np.int32)
-    if cut_every > 0:
-        i = int(rng.integers(cut_every // 2 + 1, cut_every * 3 // 2 + 2))
-        cur = 0
-        while i < n:
-            cur = (cur + 1) % len(worlds) if len(worlds) > 1 else cur
-            jump = np.array([int(rng.integers(0, world_w - w + 1)), int(rng.integers(0, world_h - h + 1))])
-            delta = jump - path[i]
-            path[i:] += delta                                   # teleport, keep the velocity plan
-            np.clip(path[i:, 0], 0, world_w - w, out=path[i:, 0])
-            np.clip(path[i:, 1], 0, world_h - h, out=path[i:, 1])
-            level[i:] = cur
-            i += int(rng.integers(cut_every // 2 + 1, cut_every * 3 // 2 + 2))
-    if frame_range is not None:
-        assert sprites == 0, "sprites are stateful; render the whole sequence"
-        a, b = frame_range
-        path, level, n = path[a:b].copy(), level[a:b].copy(), b - a
-    frames = np.empty((n, h, w), np.uint8)
-    for i in range(n):
-        x, y = int(path[i, 0]), int(path[i, 1])
-        frames[i] = worlds[level[i]][y:y + h, x:x + w]
-    if parallax > 0:
-        far = make_world(rng, world_w, world_h, n_tiles, speckle, detail)
-        band = (np.arange(h) // parallax) % 2 == 1
-        for i in range(n):
-            x, y = int(path[i, 0]) // 2, int(path[i, 1]) // 2
-            frames[i][band] = far[y:y + h, x:x + w][band]
-    if sprites > 0:
-        sw = rng.integers(12, 25, size=sprites)
-        sh = rng.integers(12, 25, size=sprites)
-        tex = [rng.integers(0, 16, size=(int(sh[k]), int(sw[k])), dtype=np.uint8) for k in range(sprites)]
-        pos = np.stack([rng.integers(0, w - 24, size=sprites), rng.integers(0, h - 24, size=sprites)], 1).astype(np.float64)
-        vel = rng.uniform(-3, 3, size=(sprites, 2))
-        for i in range(n):
-            for k in range(sprites):
-                px, py = int(pos[k, 0]), int(pos[k, 1])
-                frames[i, py:py + int(sh[k]), px:px + int(sw[k])] = tex[k][:h - py, :w - px]
-            pos += vel
-            for k in range(sprites):
-                if pos[k, 0] < 0 or pos[k, 0] > w - sw[k]:
-                    vel[k, 0] = -vel[k, 0]
-                    pos[k, 0] = min(max(pos[k, 0], 0), w - sw[k])
-                if pos[k, 1] < 0 or pos[k, 1] > h - sh[k]:
-                    vel[k, 1] = -vel[k, 1]
-                    pos[k, 1] = min(max(pos[k, 1], 0), h - sh[k])
-    return Sequence(frames=frames, path=path, level=level,
-                    meta=dict(n=n, w=w, h=h, seed=seed, n_tiles=n_tiles, speckle=speckle, vmax=tuple(vmax),
-                              sprites=sprites, cut_every=cut_every, levels=levels, parallax=parallax,
-                              detail=detail))
+    plan = TilemapPlan(n, w, h, seed, world_w=world_w, world_h=world_h, n_tiles=n_tiles, speckle=speckle, vmax=vmax,
+                       sprites=sprites, cut_every=cut_every, levels=levels, parallax=parallax, detail=detail,
+                       sprite_motion=sprite_motion)
+    a, b = frame_range if frame_range is not None else (0, n)
+    return plan.render(a, b)
 
 
 def random_frames(n: int, w: int, h: int, seed: int = 0, palette: int = 16) -> np.ndarray:
