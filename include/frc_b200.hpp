@@ -51,6 +51,10 @@ using grid_type = kpr::grid<grid_horizontal, grid_vertical, allocator_t<char>>;
 struct options {
   std::size_t batch{2048};  // frames registered per rb_register call
   int device{0};
+  // More than one entry: every batch is cut into contiguous frame ranges, one per device, and registered on all of
+  // them at once (rb_group, one context per device in this process; pair results gathered on devices[0]).  Choose
+  // `batch` as a multiple of what one GPU should see per call (e.g. 2048 x devices).  Not combined with gpu_blit.
+  std::vector<int> devices{};
   bool fill_keys{false};    // rebuild the kpr::grid for the callback from rb_keypoints
   // Map assembly on the GPU (rb_blit_blend) instead of fgm::fragment::blit per frame on the host.  All
   // frames then stay resident in the device frame store, so the sequence must fit `max_frames`; a
@@ -89,9 +93,21 @@ public:
     cfg.overlap = grid_overlap;
     cfg.weight_switch = 10; // frc::collector::match_config, src/frc.hpp:32
     cfg.region_votes = 3;   // src/frc.hpp:33
-    cfg.device = opt_.device;
+    cfg.device = opt_.devices.size() == 1 ? opt_.devices[0] : opt_.device;
 
-    if (auto rc{rb_create(&cfg, &ctx_)}; rc != RB_OK) {
+    if (opt_.devices.size() > 1) {
+      if (opt_.gpu_blit) {
+        throw std::runtime_error("frc_b200::collector: options::devices and options::gpu_blit cannot be combined");
+      }
+      std::vector<std::int32_t> devs(opt_.devices.begin(), opt_.devices.end());
+      if (auto rc{rb_group_create(&cfg, devs.data(), devs.size(), &group_)}; rc != RB_OK) {
+        std::string msg{group_ != nullptr ? rb_group_last_error(group_) : "no CUDA device"};
+        rb_group_destroy(group_);
+        group_ = nullptr;
+        throw std::runtime_error("frc_b200::collector: " + msg);
+      }
+    }
+    else if (auto rc{rb_create(&cfg, &ctx_)}; rc != RB_OK) {
       std::string msg{ctx_ != nullptr ? rb_last_error(ctx_) : "no CUDA device"};
       rb_destroy(ctx_);
       ctx_ = nullptr;
@@ -155,8 +171,16 @@ public:
       if (opt_.gpu_blit && count_ + frames.size() > std::max(opt_.max_frames, opt_.batch + 1)) {
         throw std::runtime_error("frc_b200::collector: sequence longer than options::max_frames (gpu_blit)");
       }
-      check(rb_upload(ctx_, stage_ + skip * pixels, slot0 + skip, total - skip));
-      check(rb_register(ctx_, slot0, total, offsets_, opt_.fetch_medians ? medians_ : nullptr));
+      if (group_ != nullptr) {
+        check_group(rb_group_register_host(group_, stage_, total, offsets_));
+        if (opt_.fetch_medians) {
+          check_group(rb_group_fetch_medians(group_, 0, total, medians_));
+        }
+      }
+      else {
+        check(rb_upload(ctx_, stage_ + skip * pixels, slot0 + skip, total - skip));
+        check(rb_register(ctx_, slot0, total, offsets_, opt_.fetch_medians ? medians_ : nullptr));
+      }
 
       for (std::size_t i{0}; i < frames.size(); ++i) {
         auto& frame{frames[i]};
@@ -300,7 +324,17 @@ private:
   void fill(grid_type& keys, std::size_t slot) {
     kps_.resize(dimensions_.area());
     std::size_t count{0};
-    check(rb_keypoints(ctx_, slot, kps_.data(), kps_.size(), &count));
+    if (group_ != nullptr) { // the member that owns the frame, and the frame's slot there
+      std::size_t member{0}, local{0};
+      check_group(rb_group_locate(group_, slot, &member, &local));
+      auto ctx{rb_group_context(group_, member)};
+      if (rb_keypoints(ctx, local, kps_.data(), kps_.size(), &count) != RB_OK) {
+        throw std::runtime_error(std::string{"frc_b200::collector: "} + rb_last_error(ctx));
+      }
+    }
+    else {
+      check(rb_keypoints(ctx_, slot, kps_.data(), kps_.size(), &count));
+    }
     for (std::size_t k{0}; k < count; ++k) {
       auto const& kp{kps_[k]};
       kpr::code code;
@@ -319,6 +353,12 @@ private:
     }
   }
 
+  void check_group(int rc) {
+    if (rc != RB_OK) {
+      throw std::runtime_error(std::string{"frc_b200::collector: "} + rb_group_last_error(group_));
+    }
+  }
+
   void release() noexcept {
     rb_free_host(stage_);
     rb_free_host(medians_);
@@ -327,6 +367,8 @@ private:
     offsets_ = nullptr;
     rb_destroy(ctx_);
     ctx_ = nullptr;
+    rb_group_destroy(group_);
+    group_ = nullptr;
   }
 
 private:
@@ -334,6 +376,7 @@ private:
   options opt_;
 
   rb_ctx* ctx_{nullptr};
+  rb_group* group_{nullptr};  // options::devices with more than one entry
   std::uint8_t* stage_{nullptr};
   std::uint8_t* medians_{nullptr};
   rb_offset* offsets_{nullptr};

@@ -252,6 +252,14 @@ int rb_filter_times(rb_ctx* ctx, float* ms, size_t n, uint32_t* frames_deferred)
  * (fgm::fragment::dots()).  Snippets have no rb_ctx; each owns a stream on `device`. */
 typedef struct rb_snippet rb_snippet;
 int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, rb_snippet** out);
+/* fgm::fragment::blit(pos, fragment&&) (src/fgm.hpp:99-113) + extract_single of the result (src/fgs.hpp:146-152) without
+ * leaving the device: the new snippet's W x H dot map is a's map at (ax, ay) plus b's map at (bx, by) (uint16 counters,
+ * wrapping), everything else zero.  The caller replays fragment::ensure (src/fgm.hpp:190-233) for the geometry;
+ * include/fgs_b200.hpp does.  a and b are left untouched.  rb_snippet_fetch_dots reads a snippet's map back
+ * (H * W * 16 uint16 = fgm::fragment::dots()). */
+int rb_snippet_merge(rb_snippet* a, uint32_t ax, uint32_t ay, rb_snippet* b, uint32_t bx, uint32_t by, uint32_t W, uint32_t H,
+                     rb_snippet** out);
+int rb_snippet_fetch_dots(rb_snippet* s, uint16_t* out);
 void rb_snippet_destroy(rb_snippet* s);
 const char* rb_snippet_last_error(rb_snippet* s);
 /* Parity tap: keypoint count, blend image / mask (H*W bytes each), keypoint records (unordered). Any may be NULL. */
@@ -280,6 +288,28 @@ int rb_snippet_match(rb_snippet* prev, rb_snippet* curr, uint32_t cell_w, uint32
  * if none -- the heat map after k pairs is heat0 & (first_change >= k), so aws::scan's per-frame states can be
  * replayed from one call.  (The context's width/height are the SCREEN dimensions here, src/aws.hpp:98-101.) */
 int rb_aws_compare(rb_ctx* ctx, size_t first, size_t n, uint8_t* heat, uint32_t* first_change);
+
+/* Several GPUs of ONE process: the reference's consumer, mpb::builder::collect
+ * (src/mpb.hpp:52-61), is a single C++ caller that owns the whole feed.  A group owns one rb_ctx per device;
+ * rb_group_register_host cuts the caller's n frames into contiguous ranges, one per device, with a one-frame
+ * overlap (every consecutive pair belongs to exactly one member), registers them concurrently (one host thread,
+ * one share of the packer threads and one PCIe link per member; no data-path collective), gathers the 12-byte pair
+ * results on the lead device (devices[0]) with device-to-device copies over NVLink and returns all n - 1 of them
+ * in `out` with one device-to-host copy.  cfg->device is ignored, cfg->max_frames is the capacity of the WHOLE
+ * sequence, cfg->stream must be NULL.  The frames stay resident: rb_group_range / rb_group_locate say where, and
+ * rb_group_context hands out the member for per-member calls (rb_keypoints, rb_blit_blend, rb_filter_fragment...). */
+typedef struct rb_group rb_group;
+int rb_group_create(const rb_config* cfg, const int32_t* devices, size_t ndev, rb_group** out);
+void rb_group_destroy(rb_group* g);
+const char* rb_group_last_error(rb_group* g);
+size_t rb_group_size(rb_group* g);
+rb_ctx* rb_group_context(rb_group* g, size_t member);
+int rb_group_register_host(rb_group* g, const uint8_t* frames, size_t n, rb_offset* out);
+/* member i holds frames [first, end) of the last call in its slots 0.. and OWNS frames [own, end) */
+int rb_group_range(rb_group* g, size_t member, size_t* first, size_t* end, size_t* own);
+int rb_group_locate(rb_group* g, size_t frame, size_t* member, size_t* slot);
+int rb_group_fetch_medians(rb_group* g, size_t first, size_t n, uint8_t* out);
+const rb_offset* rb_group_offsets_device(rb_group* g);  /* the gathered results on the lead device */
 
 /* Device-side access for callers that keep working on the GPU (multi-GPU gather with NCCL, map
  * assembly): the n-1 rb_offset records of the last rb_register_async, in HBM. */

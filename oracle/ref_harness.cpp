@@ -28,6 +28,9 @@
 //                                           the REFERENCE'S OWN order (top_offsets over libstdc++'s unordered_map).
 //                                           C = 1 adds (fragment, x, y) of every frame from the unmodified
 //                                           frc::collector run on the same shards (stitched at the shard borders).
+//   pairs <frames.bin> W H N <pairs.bin> <out.bin>  kpm::match of the listed consecutive pairs only (pairs.bin: uint32 indices
+//                                           i = pair (i, i + 1)); out: (valid, dx, dy) int32 per listed pair.  What
+//                                           tools/resolve_flagged.py replays the reference's own tie order with.
 //   splice <frames.bin> W H N <out.bin>     frc::collector::collect + complete, then (a) every fragment as a
 //                                           fgs snippet (blend, kpe with a 1x1 grid, src/fgs.hpp:80-89) and the
 //                                           cellular kpm::match (src/kpm.hpp:371-393) of every snippet pair with
@@ -506,6 +509,38 @@ int run_digest(int argc, char** argv) {
   return 0;
 }
 
+int run_pairs(int argc, char** argv) {
+  if (argc < 8) return 1;
+  std::size_t W = std::atoll(argv[3]), H = std::atoll(argv[4]), N = std::atoll(argv[5]);
+  auto frames = read_file(argv[2], N * W * H);
+  FILE* pf = std::fopen(argv[6], "rb");
+  if (!pf) return 2;
+  std::vector<std::uint32_t> pairs;
+  for (std::uint32_t v; std::fread(&v, 4, 1, pf) == 1;) pairs.push_back(v);
+  std::fclose(pf);
+  FILE* out = std::fopen(argv[7], "wb");
+  if (!out) return 2;
+  extractor_t extractor{mrl::dimensions_t{W, H}};
+  for (auto p : pairs) {
+    if (p + 1 >= N) { puti32(out, 0); puti32(out, 0); puti32(out, 0); continue; }
+    all::memory_stack<cpl::nat_cc> memory{};
+    memory_feed feed{frames.data(), W, H, p, p + 2};
+    auto a0{memory.previous()};
+    auto f0{feed.produce(a0)};
+    frc::image_type m0{f0.image_.dimensions(), a0};
+    auto k0{extractor.extract(f0.image_, m0, a0)};
+    all::memory_swing swing{memory};
+    pixel_alloc_t a1{swing};
+    auto f1{feed.produce(a1)};
+    frc::image_type m1{f1.image_.dimensions(), a1};
+    auto k1{extractor.extract(f1.image_, m1, a1)};
+    auto off = kpm::match(match_config{a1}, k0, k1);
+    puti32(out, off ? 1 : 0); puti32(out, off ? off->x_ : 0); puti32(out, off ? off->y_ : 0);
+  }
+  std::fclose(out);
+  return 0;
+}
+
 int run_mask(int argc, char** argv) {
   if (argc < 11) return 1;
   std::size_t bw = std::atoll(argv[3]), bh = std::atoll(argv[4]);
@@ -743,6 +778,7 @@ int main(int argc, char** argv) {
   if (mode == "dump") return run_dump(argc, argv);
   if (mode == "bench") return run_bench(argc, argv);
   if (mode == "digest") return run_digest(argc, argv);
+  if (mode == "pairs") return run_pairs(argc, argv);
   if (mode == "mask") return run_mask(argc, argv);
   if (mode == "filter") return run_filter(argc, argv);
   if (mode == "splice") return run_splice(argc, argv);

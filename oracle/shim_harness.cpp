@@ -27,7 +27,8 @@
 // fetch_medians = false): the compressed-image comparisons are skipped, the callback medians too; with filter = 1
 // only the resident pass 2 can run on such fragments.
 //
-// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1|2] [filter 0|1] [splice 0|1]   exit 0 = identical
+// usage: shim_harness <frames.bin> W H N <batch> <fill_keys 0|1> [gpu_blit 0|1|2] [filter 0|1] [splice 0|1] [devices d0,d1,...]
+//        exit 0 = identical.  devices with more than one entry: frc_b200::options::devices (rb_group, one context per device)
 
 #include <algorithm>
 #include <chrono>
@@ -170,6 +171,9 @@ int main(int argc, char** argv) {
   bool const lean = argc > 7 && std::atoi(argv[7]) == 2;
   bool const filter = argc > 8 && std::atoi(argv[8]) != 0;
   bool const splice = argc > 9 && std::atoi(argv[9]) != 0;
+  std::vector<int> devices;
+  if (argc > 10)
+    for (char const* q = argv[10]; *q;) { devices.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
   auto data = read_file(argv[1], w * h * n);
 
   std::vector<call_rec> ref_calls, gpu_calls;
@@ -192,6 +196,7 @@ int main(int argc, char** argv) {
     opt.max_frames = n;
     opt.keep_packed = !lean;
     opt.fetch_medians = !lean;
+    opt.devices = devices;
     gcol = std::make_unique<frc_b200::collector>(mrl::dimensions_t{w, h}, opt);
     memory_feed feed{data.data(), w, h, n};
     gcol->collect(feed, native_compression{}, recorder{&gpu_calls, fill});

@@ -26,6 +26,8 @@ SYMBOLS = [
     "rb_filter_fragment", "rb_filter_times", "rb_upload_medians",
     "rb_aws_compare", "rb_map_device", "rb_blend_map", "rb_map_export", "rb_blend_map_peers", "rb_sum_map_slice", "rb_blend_map_slices", "rb_snippet_create", "rb_snippet_destroy", "rb_snippet_last_error", "rb_snippet_fetch", "rb_snippet_match",
     "rb_host_lane_stats", "rb_register_host_packed4", "rb_frame_digests", "rb_fetch_ballots", "rb_matcher_kernel",
+    "rb_snippet_merge", "rb_snippet_fetch_dots", "rb_group_create", "rb_group_destroy", "rb_group_last_error", "rb_group_size", "rb_group_context", "rb_group_register_host",
+    "rb_group_range", "rb_group_locate", "rb_group_fetch_medians", "rb_group_offsets_device",
 ]
 
 
@@ -88,6 +90,10 @@ def load(build_if_missing: bool = False):
     lib.rb_filter_fragment.argtypes = [vp, vp, sz, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.rb_snippet_create.restype = C.c_int
     lib.rb_snippet_create.argtypes = [i32, vp, u32, u32, C.POINTER(vp)]
+    lib.rb_snippet_merge.restype = C.c_int
+    lib.rb_snippet_merge.argtypes = [vp, u32, u32, vp, u32, u32, u32, u32, C.POINTER(vp)]
+    lib.rb_snippet_fetch_dots.restype = C.c_int
+    lib.rb_snippet_fetch_dots.argtypes = [vp, vp]
     lib.rb_snippet_destroy.restype = None
     lib.rb_snippet_destroy.argtypes = [vp]
     lib.rb_snippet_last_error.restype = C.c_char_p
@@ -142,6 +148,26 @@ def load(build_if_missing: bool = False):
     lib.rb_device_bytes.argtypes = [vp]
     lib.rb_last_error.restype = C.c_char_p
     lib.rb_last_error.argtypes = [vp]
+    lib.rb_group_create.restype = C.c_int
+    lib.rb_group_create.argtypes = [C.POINTER(RbConfig), C.POINTER(i32), sz, C.POINTER(vp)]
+    lib.rb_group_destroy.restype = None
+    lib.rb_group_destroy.argtypes = [vp]
+    lib.rb_group_last_error.restype = C.c_char_p
+    lib.rb_group_last_error.argtypes = [vp]
+    lib.rb_group_size.restype = sz
+    lib.rb_group_size.argtypes = [vp]
+    lib.rb_group_context.restype = vp
+    lib.rb_group_context.argtypes = [vp, sz]
+    lib.rb_group_register_host.restype = C.c_int
+    lib.rb_group_register_host.argtypes = [vp, vp, sz, vp]
+    lib.rb_group_range.restype = C.c_int
+    lib.rb_group_range.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+    lib.rb_group_locate.restype = C.c_int
+    lib.rb_group_locate.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    lib.rb_group_fetch_medians.restype = C.c_int
+    lib.rb_group_fetch_medians.argtypes = [vp, sz, sz, vp]
+    lib.rb_group_offsets_device.restype = vp
+    lib.rb_group_offsets_device.argtypes = [vp]
     lib.rb_matcher_kernel.restype = C.c_char_p
     lib.rb_matcher_kernel.argtypes = [vp]
     lib.rb_offsets_device.restype = vp

@@ -349,6 +349,82 @@ CELL_MATCH_DTYPE = np.dtype([("valid", "<u4"), ("dx", "<i4"), ("dy", "<i4"), ("m
                              ("pairs", "<u8")])
 
 
+class Group:
+    """rb_group: one process, several GPUs (one rb_ctx per device), contiguous frame ranges with a one-frame
+    overlap, pair results gathered on the lead device -- the C-ABI counterpart of shard.py's torchrun path."""
+
+    def __init__(self, width, height, max_frames, devices, **kw):
+        self._lib = _lib.load()
+        cfg = _lib.RbConfig()
+        self._lib.rb_default_config(C.byref(cfg), width, height, max_frames)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        self.width, self.height, self.max_frames = width, height, max_frames
+        devs = (C.c_int32 * len(devices))(*devices)
+        self._g = C.c_void_p()
+        rc = self._lib.rb_group_create(C.byref(cfg), devs, len(devices), C.byref(self._g))
+        if rc != 0:
+            msg = self._lib.rb_group_last_error(self._g).decode() if self._g else "allocation failed"
+            if self._g:
+                self._lib.rb_group_destroy(self._g)
+                self._g = C.c_void_p()
+            raise RemapError(rc, msg)
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self._lib.rb_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RemapError(rc, self._lib.rb_group_last_error(self._g).decode())
+
+    def __len__(self):
+        return int(self._lib.rb_group_size(self._g))
+
+    def register_host(self, frames, out=None):
+        """(n, H, W) uint8 host frames -> (n - 1,) OFFSET_DTYPE of the whole sequence."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 3 and frames.shape[1:] == (self.height, self.width), frames.shape
+        n = frames.shape[0]
+        if out is None:
+            out = np.zeros(max(n - 1, 0), OFFSET_DTYPE)
+        self._check(self._lib.rb_group_register_host(self._g, frames.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p)))
+        self._keep = frames
+        return out
+
+    def range(self, member):
+        a, b, o = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._check(self._lib.rb_group_range(self._g, member, C.byref(a), C.byref(b), C.byref(o)))
+        return a.value, b.value, o.value
+
+    def fetch_medians(self, n, first=0):
+        out = np.zeros((n, self.height, self.width), np.uint8)
+        self._check(self._lib.rb_group_fetch_medians(self._g, first, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def member(self, i) -> "Registrar":
+        """A borrowed Registrar view of member i's context (do not close it)."""
+        r = Registrar.__new__(Registrar)
+        r._lib = self._lib
+        r._ctx = C.c_void_p(self._lib.rb_group_context(self._g, i))
+        r.width, r.height, r.max_frames, r.nreg = self.width, self.height, self.max_frames, 8
+        r.close = lambda: None
+        return r
+
+
 class Snippet:
     """fgs::details::extract_single (src/fgs.hpp:80-89) on the device: the blend of a fragment's dot map and the
     keypoints of kpe with a 1 x 1 grid over the whole map image.  dots: (H, W, 16) uint16."""

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, "rb_api.cu"), os.path.join(CSRC, "rb_hostpack.cpp")]
+    return [os.path.join(CSRC, "rb_api.cu"), os.path.join(CSRC, "rb_hostpack.cpp"), os.path.join(CSRC, "rb_group.cpp")]
 
 
 def deps():

@@ -1764,6 +1764,7 @@ struct rb_snippet {
   int sm_count;
   cudaStream_t stream;
   RbGeom g;
+  uint16_t* d_dots;   // the fragment's dot map (16 x uint16 per map pixel), resident: rb_snippet_merge adds maps in place
   uint8_t* d_image;   // blend image, g.pitch bytes per row
   uint8_t* d_mask;    // blend mask, W bytes per row
   uint32_t* d_kp;
@@ -1789,15 +1790,15 @@ void rb_snippet_destroy(rb_snippet* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
-  cudaFree(s->d_image); cudaFree(s->d_mask); cudaFree(s->d_kp); cudaFree(s->d_w2); cudaFree(s->d_kps); cudaFree(s->d_count);
+  cudaFree(s->d_dots); cudaFree(s->d_image); cudaFree(s->d_mask); cudaFree(s->d_kp); cudaFree(s->d_w2); cudaFree(s->d_kps); cudaFree(s->d_count);
   cudaFree(s->d_scratch);
   delete s;
 }
 
 const char* rb_snippet_last_error(rb_snippet* s) { return s ? s->err.c_str() : "null snippet"; }
 
-int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, rb_snippet** out) {
-  if (!dots || !out) return RB_ERR_INVALID;
+// a snippet object for a W x H map on `device`, dots allocated (not filled)
+static int snippet_new(int device, uint32_t W, uint32_t H, rb_snippet** out) {
   *out = nullptr;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
@@ -1810,14 +1811,18 @@ int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, 
   s->device = device;
   // kpe::extractor<kpr::grid<1, 1>, 0> (src/fgs.hpp:16,85): one region, no overlap
   if (rb_make_geom(W, H, 1, 1, 0, 10, 3, &s->g) != 0 || W >= 32768 || H >= 32768) { s->err = "unsupported map size"; return RB_ERR_INVALID; }
-  const RbGeom& g = s->g;
   RS_CUDA(s, cudaSetDevice(device));
   RS_CUDA(s, cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
   RS_CUDA(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  RS_CUDA(s, cudaMalloc(&s->d_dots, (size_t)W * H * 32));
+  return RB_OK;
+}
+
+// fgs::details::extract_single (src/fgs.hpp:80-89) over the resident dots: blend, K1 with a 1 x 1 grid, keypoint records
+static int snippet_extract(rb_snippet* s) {
+  const RbGeom& g = s->g;
+  const uint32_t W = g.W, H = g.H;
   const size_t px = (size_t)W * H, words = (size_t)H * g.NS;
-  uint16_t* d_dots = nullptr;
-  struct DotsGuard { uint16_t*& p; ~DotsGuard() { if (p) cudaFree(p); p = nullptr; } } dots_guard{d_dots};  // freed on every exit path
-  RS_CUDA(s, cudaMalloc(&d_dots, px * 32));
   RS_CUDA(s, cudaMalloc(&s->d_image, g.frame_stride + 256));
   RS_CUDA(s, cudaMalloc(&s->d_mask, px + 256));
   RS_CUDA(s, cudaMalloc(&s->d_kp, words * 4));
@@ -1827,9 +1832,8 @@ int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, 
   RS_CUDA(s, cudaMemsetAsync(s->d_kp, 0, words * 4, s->stream));
   RS_CUDA(s, cudaMemsetAsync(s->d_w2, 0, words * 4, s->stream));
   RS_CUDA(s, cudaMemsetAsync(s->d_count, 0, 64, s->stream));
-  RS_CUDA(s, cudaMemcpyAsync(d_dots, dots, px * 32, cudaMemcpyHostToDevice, s->stream));
   // fragment.blend() (src/fgs.hpp:81, src/fgm.hpp:115-135)
-  rb_blend_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(d_dots, W, H, s->d_image, g.pitch, s->d_mask);
+  rb_blend_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->d_dots, W, H, s->d_image, g.pitch, s->d_mask);
   RS_CUDA(s, cudaGetLastError());
   // extractor.extract(image, median, ...) (src/fgs.hpp:85-88): K1 on the one map image, no median output
   RbKpeParams p;
@@ -1848,13 +1852,73 @@ int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, 
   unsigned long long n = 0;
   RS_CUDA(s, cudaMemcpyAsync(&n, s->d_count, 8, cudaMemcpyDeviceToHost, s->stream));
   RS_CUDA(s, cudaStreamSynchronize(s->stream));
-  cudaFree(d_dots);
-  d_dots = nullptr;
   s->nkp = (uint32_t)n;
   RS_CUDA(s, cudaMalloc(&s->d_kps, ((size_t)n + 1) * sizeof(RbSnipKp)));
   uint32_t* cnt = reinterpret_cast<uint32_t*>(s->d_count + 1);
   rb_snip_emit_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(g, s->d_image, s->d_kp, s->d_w2, s->d_kps, s->nkp, cnt);
   RS_CUDA(s, cudaGetLastError());
+  RS_CUDA(s, cudaStreamSynchronize(s->stream));
+  return RB_OK;
+}
+
+int rb_snippet_create(int device, const uint16_t* dots, uint32_t W, uint32_t H, rb_snippet** out) {
+  if (!dots || !out) return RB_ERR_INVALID;
+  const int rc = snippet_new(device, W, H, out);
+  if (rc != RB_OK) return rc;
+  rb_snippet* s = *out;
+  RS_CUDA(s, cudaMemcpyAsync(s->d_dots, dots, (size_t)W * H * 32, cudaMemcpyHostToDevice, s->stream));
+  return snippet_extract(s);
+}
+
+// fgm::fragment::blit(pos, fragment&&) (src/fgm.hpp:99-113) on the device: out's W x H map is zero except for a's map
+// at (ax, ay) plus b's map at (bx, by), uint16 counters adding with wrap-around like the reference's `+=` on
+// std::uint16_t; then extract_single over the merged map (src/fgs.hpp:146-152).  The caller computes the geometry
+// (fragment::ensure / extend, src/fgm.hpp:190-233; include/fgs_b200.hpp does).  a and b stay valid.
+__global__ void __launch_bounds__(256) rb_dots_place_kernel(const uint4* __restrict__ src, uint32_t sW, uint32_t sH, uint4* __restrict__ dst,
+                                                            uint32_t dW, uint32_t ox, uint32_t oy, int add) {
+  const size_t total = (size_t)sW * sH * 2;  // two 16-byte halves per dot
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pxl = i >> 1;
+    const uint32_t y = (uint32_t)(pxl / sW), x = (uint32_t)(pxl - (size_t)y * sW);
+    const size_t at = (((size_t)(y + oy) * dW + (x + ox)) << 1) | (i & 1);
+    uint4 v = __ldg(src + i);
+    if (add) {
+      const uint4 d = dst[at];
+      v.x = __vadd2(v.x, d.x); v.y = __vadd2(v.y, d.y); v.z = __vadd2(v.z, d.z); v.w = __vadd2(v.w, d.w);  // per-halfword, wrapping
+    }
+    dst[at] = v;
+  }
+}
+
+int rb_snippet_merge(rb_snippet* a, uint32_t ax, uint32_t ay, rb_snippet* b, uint32_t bx, uint32_t by, uint32_t W, uint32_t H,
+                     rb_snippet** out) {
+  if (!a || !b || !out) return RB_ERR_INVALID;
+  *out = nullptr;
+  if (a->device != b->device) { a->err = "rb_snippet_merge: snippets on different devices"; return RB_ERR_INVALID; }
+  if ((uint64_t)ax + a->g.W > W || (uint64_t)ay + a->g.H > H || (uint64_t)bx + b->g.W > W || (uint64_t)by + b->g.H > H) {
+    a->err = "rb_snippet_merge: a map lies outside the merged map";
+    return RB_ERR_INVALID;
+  }
+  const int rc = snippet_new(a->device, W, H, out);
+  if (rc != RB_OK) return rc;
+  rb_snippet* s = *out;
+  RS_CUDA(s, cudaStreamSynchronize(a->stream));
+  RS_CUDA(s, cudaStreamSynchronize(b->stream));
+  RS_CUDA(s, cudaMemsetAsync(s->d_dots, 0, (size_t)W * H * 32, s->stream));
+  const uint32_t grid = (uint32_t)s->sm_count * 8;
+  rb_dots_place_kernel<<<grid, 256, 0, s->stream>>>(reinterpret_cast<const uint4*>(a->d_dots), a->g.W, a->g.H,
+                                                    reinterpret_cast<uint4*>(s->d_dots), W, ax, ay, 0);
+  rb_dots_place_kernel<<<grid, 256, 0, s->stream>>>(reinterpret_cast<const uint4*>(b->d_dots), b->g.W, b->g.H,
+                                                    reinterpret_cast<uint4*>(s->d_dots), W, bx, by, 1);
+  RS_CUDA(s, cudaGetLastError());
+  return snippet_extract(s);
+}
+
+// The snippet's dot map (H * W * 16 uint16): what fgm::fragment::dots() holds after the merges.
+int rb_snippet_fetch_dots(rb_snippet* s, uint16_t* out) {
+  if (!s || !out) return RB_ERR_INVALID;
+  RS_CUDA(s, cudaSetDevice(s->device));
+  RS_CUDA(s, cudaMemcpyAsync(out, s->d_dots, (size_t)s->g.W * s->g.H * 32, cudaMemcpyDeviceToHost, s->stream));
   RS_CUDA(s, cudaStreamSynchronize(s->stream));
   return RB_OK;
 }

@@ -228,6 +228,16 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
       request(0);
       if (nsteps > 1) request(1);
     }
+    // entry i of step t's list: weight-2 entries sit at the front of the list row, weight-1 entries at its end
+    // (rb_prep.cuh).  Every worker's FIRST entry of a step is requested during the step before, so that no step
+    // opens with a round trip to L2 / HBM; later entries one trip ahead.
+    auto list_entry = [&](uint32_t t, uint32_t i) -> uint32_t {
+      const uint32_t wl = s.planL[t], L = wl & 0xFFFFu, nw2 = wl >> 16;
+      if (i >= L) return 0u;
+      const uint32_t* row = p.lists + ((uint64_t)(fa + t) * g.nreg + region) * p.lcap;
+      return __ldg(row + (i < nw2 ? i : p.lcap - 1 - (i - nw2)));
+    };
+    uint32_t pfirst = ballot_warp ? 0u : list_entry(0, tid);
 
     for (uint32_t t = 0; t < nsteps; ++t) {
       const uint32_t st = t & 1, stage = t % 3;
@@ -237,6 +247,8 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
           for (uint32_t i = tid; i < p.tslots / 4; i += NTP) hc[i] = make_uint4(NIL, NIL, NIL, NIL);
           workers_sync();
         }
+        const uint32_t pcur = pfirst;                          // this worker's first entry of step t
+        if (t + 1 < nsteps) pfirst = list_entry(t + 1, tid);  // ... and of step t + 1: lands while this step works
         mbar_wait(&s.mbar[stage], (phbits >> stage) & 1u, p.work_counter + 2);
         phbits ^= 1u << stage;
         const uint32_t fl = s.planF[t];
@@ -269,11 +281,10 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
             }
           };
           const uint32_t obias = (p.bias_x << p.dybits) | p.bias_y;
-          // weight-2 entries sit at the front of the list row, weight-1 entries at its end (rb_prep.cuh)
           const uint32_t* row = p.lists + ((uint64_t)(fa + t) * g.nreg + region) * p.lcap;
           auto list_at = [&](uint32_t i) { return i < L ? __ldg(row + (i < nw2 ? i : p.lcap - 1 - (i - nw2))) : 0u; };
           const uint32_t Lw = (L + 31) & ~31u;  // whole warps iterate together
-          uint32_t pnext = list_at(tid);
+          uint32_t pnext = pcur;
           for (uint32_t i = tid; i < Lw; i += NTP) {
             const uint32_t pw = pnext;
             pnext = list_at(i + NTP);

@@ -68,3 +68,25 @@ def test_config5_cuts_and_parallax():
 def test_heavy_ties_16px_parallax():
     """16-px parallax bands: the workload where SURVEY.md App. C saw declared offsets depend on the tie order."""
     _run("parallax16_3000", synth.scrolling_tilemap(3000, 320, 224, seed=6, parallax=16))
+
+
+def test_flagged_pairs_resolved_offline_equal_the_reference_everywhere():
+    """tools/resolve_flagged.py replays the flagged pairs through the compiled reference: afterwards every declared
+    offset of the sequence equals the reference's (the flag is conservative and complete)."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import resolve_flagged
+    from remap_b200 import RB_OFFSET_VALID
+    n, W, H = 1500, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=6, parallax=16)
+    ref = digest_check.ref_digest(seq.frames, collector=False)
+    with remap_b200.Registrar(W, H, max_frames=n) as reg:
+        reg.upload(seq.frames)
+        off, _ = reg.register(n)
+    patched, info = resolve_flagged.resolve(seq.frames, off)
+    assert info["flagged"] > 0, "the workload should hold tie-sensitive pairs"
+    rvalid = ref["pairs"]["valid"] != 0
+    assert np.array_equal((patched["flags"] & RB_OFFSET_VALID) != 0, rvalid)
+    assert np.array_equal(patched["dx"][rvalid], ref["pairs"]["dx"][rvalid])
+    assert np.array_equal(patched["dy"][rvalid], ref["pairs"]["dy"][rvalid])
+    _record("parallax16_resolved_1500", **info)

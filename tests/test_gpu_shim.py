@@ -18,14 +18,16 @@ SHIM = os.path.join(ROOT, "oracle", "_ref", "shim_harness")
 pytestmark = pytest.mark.gpu
 
 
-def _run(frames, batch, fill, tmp_path, gpu_blit=False, filter=False):
+def _run(frames, batch, fill, tmp_path, gpu_blit=False, filter=False, devices=None):
     if not os.path.exists(SHIM):
         pytest.fail("oracle/_ref/shim_harness missing: run `python oracle/build_ref.py` in the build container")
     n, H, W = frames.shape
     path = os.path.join(tmp_path, "frames.bin")
     np.ascontiguousarray(frames, np.uint8).tofile(path)
-    r = subprocess.run([SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill)), str(int(gpu_blit)), str(int(filter))], capture_output=True,
-                       text=True, timeout=600)
+    cmd = [SHIM, path, str(W), str(H), str(n), str(batch), str(int(fill)), str(int(gpu_blit)), str(int(filter))]
+    if devices:
+        cmd += ["0", ",".join(str(d) for d in devices)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-500:], r.stderr[-500:])
     assert "\nIDENTICAL" in "\n" + r.stdout, r.stdout
     return r.stdout[r.stdout.index("IDENTICAL"):] if not filter else r.stdout
@@ -65,6 +67,17 @@ def test_collector_shim_gpu_blit_with_keys_across_batches(tmp_path):
     seq = synth.scrolling_tilemap(40, 320, 224, seed=17)
     out = _run(seq.frames, 9, True, str(tmp_path), gpu_blit=True)
     assert "keys compared" in out and "dots from rb_blit_blend" in out, out
+
+
+@pytest.mark.parametrize("members,batch", [(2, 64), (3, 25), (8, 200)])
+def test_collector_shim_over_several_devices(members, batch, tmp_path):
+    """options::devices: every batch is split over the members of an rb_group (one context per device; on a one-GPU
+    box they share cuda:0) -- fragments, positions, compressed medians, callbacks and keys as the reference's."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    seq = synth.scrolling_tilemap(130, 320, 224, seed=19, cut_every=50)
+    out = _run(seq.frames, batch, True, str(tmp_path), devices=[i % ngpu for i in range(members)])
+    assert "130 frames" in out and "keys compared" in out, out
 
 
 def test_filter_shim_matches_reference_fdf_filter(tmp_path):
