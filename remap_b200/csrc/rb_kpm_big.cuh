@@ -43,7 +43,7 @@ struct Smem {
   uint8_t* tile;      // [3][tile_bytes] packed 4 bit/pixel tiles; frame t of a run lives in stage t % 3
   uint16_t* pos;      // [2][cap] tile-relative position of entry i: (x - 2 - tx0) | (y - Y0) << 8
   uint32_t* link;     // [2][cap] next entry of the bucket (NIL16: none) | hash tag << 16
-  uint32_t* head;     // [2][tslots] first entry of each bucket's chain, or NIL
+  uint32_t* head;     // [2][tslots] epoch << 16 | first entry of the bucket's chain (valid only for the frame of that epoch)
   uint32_t* otab;     // [2][oslots] offset id << cntbits | count, or EMPTY
   uint16_t* touched;  // [2][oslots]
   uint32_t* planL;    // [run + 3] entries taking part | weight-2 entries << 16
@@ -109,11 +109,15 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (uint32_t i = tid; i < 2 * p.tslots; i += NT) s.head[i] = NIL;
+  for (uint32_t i = tid; i < 2 * p.tslots; i += NT) s.head[i] = 0;  // epoch 0: never a frame's epoch
   for (uint32_t i = tid; i < 2 * p.oslots; i += NT) s.otab[i] = EMPTY;
   if (tid < 8) s.ctl[tid] = 0;
   __syncthreads();
   uint32_t phbits = 0;  // mbarrier phase parities, bit per stage (persist across work items)
+  // Bucket heads are never cleared: a head word is (epoch << 16 | entry), every frame a CTA builds gets the next
+  // epoch, and a head whose epoch is not the frame's is an empty bucket.  (Clearing cost a pass over the table and a
+  // second barrier per step.)  The 16-bit epoch wraps after 65,535 frames: then both tables are zeroed once.
+  uint32_t ebase = 1;
 
   // ---- the ballot warp's job: one finished offset table -> one RbRegionVote (as in rb_kpm_fast_kernel) --------
   auto make_ballot = [&](uint32_t t, uint32_t fa, uint32_t region) {
@@ -217,6 +221,11 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
     }
     __syncthreads();
 
+    if (ebase + nsteps > 0xFFFFu) {  // block-uniform
+      for (uint32_t i = tid; i < 2 * p.tslots; i += NT) s.head[i] = 0;
+      ebase = 1;
+      __syncthreads();
+    }
     auto request = [&](uint32_t t) {  // thread 0 only: the tile of step t into stage t % 3
       const uint32_t stage = t % 3;
       mbar_expect_tx(&s.mbar[stage], p.box_x * p.box_y * p.nbox_y);
@@ -242,11 +251,6 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
     for (uint32_t t = 0; t < nsteps; ++t) {
       const uint32_t st = t & 1, stage = t % 3;
       if (!ballot_warp) {
-        if (t >= 2) {  // table st holds the chains of frame t - 2 (probed for the last time in step t - 1)
-          uint4* hc = reinterpret_cast<uint4*>(s.head + st * p.tslots);
-          for (uint32_t i = tid; i < p.tslots / 4; i += NTP) hc[i] = make_uint4(NIL, NIL, NIL, NIL);
-          workers_sync();
-        }
         const uint32_t pcur = pfirst;                          // this worker's first entry of step t
         if (t + 1 < nsteps) pfirst = list_entry(t + 1, tid);  // ... and of step t + 1: lands while this step works
         mbar_wait(&s.mbar[stage], (phbits >> stage) & 1u, p.work_counter + 2);
@@ -284,35 +288,67 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
           const uint32_t* row = p.lists + ((uint64_t)(fa + t) * g.nreg + region) * p.lcap;
           auto list_at = [&](uint32_t i) { return i < L ? __ldg(row + (i < nw2 ? i : p.lcap - 1 - (i - nw2))) : 0u; };
           const uint32_t Lw = (L + 31) & ~31u;  // whole warps iterate together
+          const uint32_t ecur = (ebase + t) << 16, eprev = (ebase + t - 1) << 16;
+          // re-forms the code of previous-frame entry j from the previous tile and compares: the offset id, or NONE
+          auto verify = [&](uint32_t j, const Code& c, uint32_t key) -> uint32_t {
+            const uint32_t pp = ppos[j], plx = pp & 0xFFu, ply = pp >> 8;
+            const Code d = code_at(ptile, wpr, plx, ply);
+            if (d.c0 == c.c0 && d.c1 == c.c1 && d.c2 == c.c2 && d.c3 == c.c3)
+              return ((plx << p.dybits) | ply) - key + obias;  // equal codes: prev - curr (src/kpm.hpp:96-98)
+            return NONE;
+          };
           uint32_t pnext = pcur;
           for (uint32_t i = tid; i < Lw; i += NTP) {
             const uint32_t pw = pnext;
             pnext = list_at(i + NTP);
             uint32_t oid0 = NONE | lane, oid1 = NONE | lane;  // unique per lane: groups of one in match_any
+            // The bucket walk only COLLECTS the entries whose 16-bit tag matches (lanes leave the walk at different
+            // trips); the expensive part -- re-forming the previous keypoint's code from the tile -- runs after the
+            // walk with the warp converged again.  A third tag hit (rare: heavy repetition) takes the slow path.
+            uint32_t cand0 = NIL16, cand1 = NIL16, key = 0, jhead = NIL16, tag = 0;
+            bool more = false;
+            Code c;
+            c.c0 = c.c1 = c.c2 = c.c3 = 0;
             if (i < L) {
               const uint32_t lx = (pw & 0x7FFFu) - 2 - tx0, ly = (pw >> 16) - Y0;
-              const Code c = code_at(tile, wpr, lx, ly);
-              const uint32_t h = code_hash(c), slot = h & tmask, tag = h & 0xFFFF0000u;
-              const uint32_t key = (lx << p.dybits) | ly;
+              c = code_at(tile, wpr, lx, ly);
+              const uint32_t h = code_hash(c), slot = h & tmask;
+              tag = h & 0xFFFF0000u;
+              key = (lx << p.dybits) | ly;
               pos[i] = (uint16_t)(lx | (ly << 8));
-              link[i] = (atomicExch(&head[slot], i) & 0xFFFFu) | tag;  // push onto the bucket's chain (NIL -> NIL16)
+              const uint32_t old = atomicExch(&head[slot], ecur | i);  // push onto the bucket's chain
+              link[i] = ((old & 0xFFFF0000u) == ecur ? (old & 0xFFFFu) : NIL16) | tag;
               if (pair_ok && (use_all || (pw & 0x8000u))) {  // !use_all: weight-2 codes only (src/kpm.hpp:113-117)
-                uint32_t j = phead[slot];
-                while (j != NIL) {
+                const uint32_t ph = phead[slot];
+                jhead = (ph & 0xFFFF0000u) == eprev ? (ph & 0xFFFFu) : NIL16;
+                uint32_t j = jhead;
+                while (j != NIL16) {
                   const uint32_t e = plink[j];
                   if ((e & 0xFFFF0000u) == tag) {
-                    const uint32_t pp = ppos[j], plx = pp & 0xFFu, ply = pp >> 8;
-                    const Code d = code_at(ptile, wpr, plx, ply);
-                    if (d.c0 == c.c0 && d.c1 == c.c1 && d.c2 == c.c2 && d.c3 == c.c3) {
-                      // equal codes: vote prev - curr (src/kpm.hpp:96-98)
-                      const uint32_t oid = ((plx << p.dybits) | ply) - key + obias;
-                      if (oid0 & NONE) oid0 = oid;
-                      else if (oid1 & NONE) oid1 = oid;
-                      else vote(oid, 1u);  // third and later matches of one keypoint: rare, one by one
-                    }
+                    if (cand0 == NIL16) cand0 = j;
+                    else if (cand1 == NIL16) cand1 = j;
+                    else more = true;
                   }
-                  const uint32_t nx = e & 0xFFFFu;
-                  j = nx == NIL16 ? NIL : nx;
+                  j = e & 0xFFFFu;
+                }
+              }
+            }
+            if (cand0 != NIL16) oid0 = verify(cand0, c, key);
+            if (oid0 & NONE) oid0 = NONE | lane;
+            if (__any_sync(0xffffffffu, cand1 != NIL16)) {
+              if (cand1 != NIL16) {
+                const uint32_t o = verify(cand1, c, key);
+                if (!(o & NONE)) { if (oid0 & NONE) oid0 = o; else oid1 = o; }
+              }
+              if (more) {  // third and later tag hits of one keypoint: one by one
+                uint32_t seen = 0;
+                for (uint32_t j = jhead; j != NIL16;) {
+                  const uint32_t e = plink[j];
+                  if ((e & 0xFFFF0000u) == tag && ++seen > 2) {
+                    const uint32_t o = verify(j, c, key);
+                    if (!(o & NONE)) vote(o, 1u);
+                  }
+                  j = e & 0xFFFFu;
                 }
               }
             }
@@ -333,10 +369,7 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
       if (tid == 0 && t + 2 < nsteps) request(t + 2);  // into the stage frame t - 1 occupied
     }
     if (ballot_warp && nsteps >= 2) make_ballot(nsteps - 1, fa, region);
-    if (!ballot_warp) {  // both bucket tables may be filled: the next work item starts clean
-      uint4* h = reinterpret_cast<uint4*>(s.head);
-      for (uint32_t i = tid; i < 2 * p.tslots / 4; i += NTP) h[i] = make_uint4(NIL, NIL, NIL, NIL);
-    }
+    ebase += nsteps;  // the next work item's frames get fresh epochs: its tables start out empty without a clear
   }
 }
 

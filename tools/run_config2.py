@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""BASELINE configs[3] in small: 640x480, large scroll offsets, dense keypoints (for ncu captures)."""
+"""BASELINE configs[1] in small (for ncu captures): 320x224, n frames, two registrations."""
 import os
 import sys
 
@@ -8,9 +8,9 @@ sys.path.insert(0, ROOT)
 import remap_b200  # noqa: E402
 from remap_b200 import synth  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-seq = synth.scrolling_tilemap(n, 640, 480, seed=4, speckle=0.10, vmax=(48, 48))
-with remap_b200.Registrar(640, 480, max_frames=n, profile=True) as reg:
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+seq = synth.scrolling_tilemap(n, 320, 224, seed=1)
+with remap_b200.Registrar(320, 224, max_frames=n, profile=True) as reg:
     reg.upload(seq.frames)
     for _ in range(2):
         off, _ = reg.register(n)
