@@ -330,7 +330,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a rank that dies or a mismatched collective must end the run in minutes, not hold the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     seq, total_frames = make_shard(args, rank, world)
     n = seq.frames.shape[0]
@@ -394,9 +396,10 @@ def main():
     timed_samples = len(sampler.lines)
     # the timed region of a default run lasts ~50 ms and one NVML query takes a few ms: keep the same load running
     # (untimed) until the sampler holds >= 20 samples under load
+    # (this rank's kernels only -- no collective: the ranks take different numbers of trips here)
     t_top = time.perf_counter()
     while len(sampler.lines) < 24 and time.perf_counter() - t_top < 3.0:
-        step()
+        reg.register_async(n)
         torch.cuda.synchronize(dev)
     sync_all()
     clocks = sampler.stop()

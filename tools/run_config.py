@@ -62,7 +62,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=900))
 
     cfgd = bench.CONFIGS[args.config]
     W, H, gen = cfgd["width"], cfgd["height"], dict(cfgd["gen"])
