@@ -225,7 +225,8 @@ def main():
             width=W, height=H,
             value=total / dev_s, unit="frames/s", device_seconds=dev_s,
             e2e=dict(value=total / e2e_s, seconds=e2e_s, lanes_rank0=lanes),
-            roofline=dict(frac_path=b_path * total / dev_s / 1e9 / peak, bytes_per_frame=b_path, keypoints_per_frame=kpf, peak=peak,
+            roofline=dict(frac_path=b_path * total / dev_s / 1e9 / (peak * world),  # per GPU: N GPUs move N x the bytes
+                           bytes_per_frame=b_path, keypoints_per_frame=kpf, peak=peak,
                           peak_source=peak_src, kernel_ms_rank0={k: v for k, v in kt_sum.items()}),
             parity=dict(against="oracle/_ref/ref_harness digest (the reference's own kpe::extractor::extract, kpm::match, "
                                 "count_offsets, top_offsets) on the same frames",
