@@ -24,7 +24,10 @@
 #include "fgm.hpp"
 #include "kpm.hpp"
 
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <iterator>
 #include <list>
 #include <stdexcept>
@@ -124,6 +127,13 @@ namespace details {
 template<typename Iter>
 [[nodiscard]] std::vector<fgm::fragment> splice(Iter first, Iter last, options const& opt = options{}) {
   using namespace details;
+  // RB_SPLICE_TRACE=1: wall time per phase on stderr (where a splice spends its time; measurements only)
+  bool const trace{std::getenv("RB_SPLICE_TRACE") != nullptr};
+  double t_extract{0}, t_match{0}, t_merge{0}, t_fetch{0};
+  auto now{[] { return std::chrono::steady_clock::now(); }};
+  auto since{[](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }};
   std::list<node> nodes;
   std::size_t next_id{0};
   struct cleanup {
@@ -133,13 +143,17 @@ template<typename Iter>
     }
   } guard{nodes};
 
+  auto t0{now()};
   for (; first != last; ++first) {  // extract_all
     nodes.push_back(node{next_id++, std::move(*first)});
     extract(nodes.back(), opt);
   }
+  t_extract += since(t0);
+  t0 = now();
   for (auto head{nodes.begin()}; head != nodes.end(); ++head) {  // match_all
     for (auto other{std::next(head)}; other != nodes.end(); ++other) match(*head, *other, opt);
   }
+  t_match += since(t0);
 
   while (true) {
     // select_match: first edge with the largest count, snippets in list order, edges in creation order
@@ -156,6 +170,7 @@ template<typename Iter>
     if (pick == nullptr) break;
 
     // splice_single: dst.blit(dst.zero() + offset, std::move(right.fragment)); dst.normalize()  (src/fgs.hpp:146-150)
+    t0 = now();
     auto right{nodes.begin()};
     while (right->id != pick->other) ++right;
     auto offset{pick->vote.offset_};
@@ -197,8 +212,12 @@ template<typename Iter>
       std::erase_if(n.edges, [&](edge const& e) { return e.other == gone_a || e.other == gone_b; });
     }
     nodes.push_front(std::move(merged));
+    t_merge += since(t0);
+    t0 = now();
     for (auto other{std::next(nodes.begin())}; other != nodes.end(); ++other) match(nodes.front(), *other, opt);
+    t_match += since(t0);
   }
+  t0 = now();
 
   std::vector<fgm::fragment> result{};
   result.reserve(nodes.size());
@@ -212,6 +231,11 @@ template<typename Iter>
       fail(n.snippet, "rb_snippet_fetch_dots");
     }
     result.emplace_back(std::move(dots), n.step, n.zero, std::move(n.frames));
+  }
+  t_fetch += since(t0);
+  if (trace) {
+    std::fprintf(stderr, "fgs_b200::splice: extract (upload + blend + kpe) %.1f ms, matches %.1f ms, merges %.1f ms, read-back %.1f ms\n",
+                 t_extract, t_match, t_merge, t_fetch);
   }
   return result;
 }

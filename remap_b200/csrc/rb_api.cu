@@ -666,10 +666,12 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
       B.bias_y = maxh;
       big_ok = big_ok && lxmax <= 255 && maxh <= 256 && B.offbits <= 19;  // 16-bit positions; >= 13 bits of count per bin
       const uint32_t cntmax_b = (1u << (32 - B.offbits)) - 1u;
-      B.oslots = 2048;
+      B.oslots = 1024;  // 2 x 6 KB; a region whose pair has more distinct offsets (scene cuts, heavy repetition) is deferred
       B.cap = 0;
-      // the largest bucket table whose lists still hold what a dense frame puts into a region (~ a keypoint per 6 pixels)
-      const uint32_t want = cfg->list_cap ? cfg->list_cap : maxcols * maxh / 6;
+      // the largest bucket table whose lists still hold what a dense frame puts into a region (~ a keypoint per 8 pixels;
+      // BASELINE configs[3] has one per 9): short chains matter more than the last thousand entries of capacity --
+      // the bucket walk's trip count is the longest chain among a warp's 32 keypoints
+      const uint32_t want = cfg->list_cap ? cfg->list_cap : maxcols * maxh / 8;
       for (uint32_t ts = 8192; big_ok && ts >= 1024; ts >>= 1) {
         B.tslots = ts;
         B.cap = 0;

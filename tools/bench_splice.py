@@ -32,6 +32,9 @@ def main():
     m = re.search(r"fgs::splice ([0-9.]+) ms, fgs_b200::splice ([0-9.]+) ms", res["shim_harness"])
     if m:
         res["reference_ms"], res["b200_ms"] = float(m.group(1)), float(m.group(2))
+    tr = [l for l in r.stderr.splitlines() if l.startswith("fgs_b200::splice:")]
+    if tr:
+        res["phases"] = tr[-1]  # RB_SPLICE_TRACE=1
     # large maps: two overlapping 2400x1600 crops of one world
     rng = np.random.default_rng(7)
     world = synth.make_world(rng, 4096, 2048, n_tiles=64, speckle=0.05)
