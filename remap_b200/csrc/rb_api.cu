@@ -664,6 +664,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
       B.offbits = dxb + dyb;
       B.bias_x = maxcols;
       B.bias_y = maxh;
+      B.epoch0 = getenv("RB_BIG_EPOCH0") ? (uint32_t)atoi(getenv("RB_BIG_EPOCH0")) : 1u;  // tests: start near the 16-bit wrap
       big_ok = big_ok && lxmax <= 255 && maxh <= 256 && B.offbits <= 19;  // 16-bit positions; >= 13 bits of count per bin
       const uint32_t cntmax_b = (1u << (32 - B.offbits)) - 1u;
       B.oslots = 1024;  // 2 x 6 KB; a region whose pair has more distinct offsets (scene cuts, heavy repetition) is deferred
@@ -1797,12 +1798,32 @@ struct rb_snippet {
     }                                                                                           \
   } while (0)
 
+// Snippet buffers come from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync, with the pool told to keep
+// what is freed): a splice creates and destroys a snippet per merge, and plain cudaMalloc / cudaFree (milliseconds each
+// for 100 MB maps, plus a device-wide synchronisation per free) cost more than the merge's kernels.
+static cudaError_t snip_alloc(rb_snippet* s, void** p, size_t bytes) { return cudaMallocAsync(p, bytes, s->stream); }
+static void snip_free(rb_snippet* s, void* p) { if (p) cudaFreeAsync(p, s->stream); }
+static void snip_pool_setup(int device) {
+  static std::atomic<unsigned long long> done{0};
+  if (device < 0 || device >= 64 || (done.load() >> device) & 1ull) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  cudaGetLastError();
+  done.fetch_or(1ull << device);
+}
+
 void rb_snippet_destroy(rb_snippet* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  if (s->stream) { cudaStreamSynchronize(s->stream); cudaStreamDestroy(s->stream); }
-  cudaFree(s->d_dots); cudaFree(s->d_image); cudaFree(s->d_mask); cudaFree(s->d_kp); cudaFree(s->d_w2); cudaFree(s->d_kps); cudaFree(s->d_count);
-  cudaFree(s->d_scratch);
+  if (s->stream) {
+    snip_free(s, s->d_dots); snip_free(s, s->d_image); snip_free(s, s->d_mask); snip_free(s, s->d_kp); snip_free(s, s->d_w2);
+    snip_free(s, s->d_kps); snip_free(s, s->d_count); snip_free(s, s->d_scratch);
+    cudaStreamSynchronize(s->stream);
+    cudaStreamDestroy(s->stream);
+  }
   delete s;
 }
 
@@ -1825,7 +1846,8 @@ static int snippet_new(int device, uint32_t W, uint32_t H, rb_snippet** out) {
   RS_CUDA(s, cudaSetDevice(device));
   RS_CUDA(s, cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device));
   RS_CUDA(s, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-  RS_CUDA(s, cudaMalloc(&s->d_dots, (size_t)W * H * 32));
+  snip_pool_setup(device);
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_dots), (size_t)W * H * 32));
   return RB_OK;
 }
 
@@ -1834,11 +1856,11 @@ static int snippet_extract(rb_snippet* s) {
   const RbGeom& g = s->g;
   const uint32_t W = g.W, H = g.H;
   const size_t px = (size_t)W * H, words = (size_t)H * g.NS;
-  RS_CUDA(s, cudaMalloc(&s->d_image, g.frame_stride + 256));
-  RS_CUDA(s, cudaMalloc(&s->d_mask, px + 256));
-  RS_CUDA(s, cudaMalloc(&s->d_kp, words * 4));
-  RS_CUDA(s, cudaMalloc(&s->d_w2, words * 4));
-  RS_CUDA(s, cudaMalloc(&s->d_count, 64));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_image), g.frame_stride + 256));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_mask), px + 256));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_kp), words * 4));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_w2), words * 4));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_count), 64));
   RS_CUDA(s, cudaMemsetAsync(s->d_image, 0, g.frame_stride + 256, s->stream));
   RS_CUDA(s, cudaMemsetAsync(s->d_kp, 0, words * 4, s->stream));
   RS_CUDA(s, cudaMemsetAsync(s->d_w2, 0, words * 4, s->stream));
@@ -1864,7 +1886,7 @@ static int snippet_extract(rb_snippet* s) {
   RS_CUDA(s, cudaMemcpyAsync(&n, s->d_count, 8, cudaMemcpyDeviceToHost, s->stream));
   RS_CUDA(s, cudaStreamSynchronize(s->stream));
   s->nkp = (uint32_t)n;
-  RS_CUDA(s, cudaMalloc(&s->d_kps, ((size_t)n + 1) * sizeof(RbSnipKp)));
+  RS_CUDA(s, snip_alloc(s, reinterpret_cast<void**>(&s->d_kps), ((size_t)n + 1) * sizeof(RbSnipKp)));
   uint32_t* cnt = reinterpret_cast<uint32_t*>(s->d_count + 1);
   rb_snip_emit_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(g, s->d_image, s->d_kp, s->d_w2, s->d_kps, s->nkp, cnt);
   RS_CUDA(s, cudaGetLastError());
@@ -2005,10 +2027,10 @@ int rb_snippet_match(rb_snippet* a, rb_snippet* b, uint32_t cell_w, uint32_t cel
   const size_t actwords = ((size_t)p.AW * (p.cH / cell_h + 1) + 31) / 32;
   const size_t bytes = ((size_t)p.nbuckets + p.np + nbins + cellwords + actwords) * 4 + 64;
   if (bytes > a->scratch_cap) {  // cudaMalloc / cudaFree per match cost more than the match itself
-    cudaFree(a->d_scratch);
+    snip_free(a, a->d_scratch);
     a->d_scratch = nullptr;
     a->scratch_cap = 0;
-    RS_CUDA(a, cudaMalloc(&a->d_scratch, bytes));
+    RS_CUDA(a, snip_alloc(a, reinterpret_cast<void**>(&a->d_scratch), bytes));
     a->scratch_cap = bytes;
   }
   uint8_t* mem = a->d_scratch;

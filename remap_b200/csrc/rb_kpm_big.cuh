@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(RB_BIG_NT, 1) rb_kpm_big_kernel(const __grid_c
   // Bucket heads are never cleared: a head word is (epoch << 16 | entry), every frame a CTA builds gets the next
   // epoch, and a head whose epoch is not the frame's is an empty bucket.  (Clearing cost a pass over the table and a
   // second barrier per step.)  The 16-bit epoch wraps after 65,535 frames: then both tables are zeroed once.
-  uint32_t ebase = 1;
+  uint32_t ebase = p.epoch0 >= 1 && p.epoch0 < 0xFFFFu ? p.epoch0 : 1u;
 
   // ---- the ballot warp's job: one finished offset table -> one RbRegionVote (as in rb_kpm_fast_kernel) --------
   auto make_ballot = [&](uint32_t t, uint32_t fa, uint32_t region) {

@@ -55,6 +55,7 @@ struct RbKpmFastParams {
   uint32_t nbox_y;         // boxes stacked vertically per tile (tile rows = nbox_y * box_y)
   uint32_t dybits, offbits;  // offset id = (dx + W) << dybits | (dy + H), offbits bits in all
   uint32_t bias_x, bias_y;   // rb_kpm_big_kernel only: offset id = (dx + bias_x) << dybits | (dy + bias_y)
+  uint32_t epoch0;           // rb_kpm_big_kernel only: first bucket-head epoch of a launch (1; tests start near the wrap)
   const uint2* items;      // nullptr: work item i = (region i % nreg, run i / nreg).  Otherwise a second pass
   const uint32_t* nitems;  //   over (pair, region) entries another launch deferred: item i = items[i], one pair each
   uint32_t* work_counter;  // [0] work items, [2] error word; zeroed before launch

@@ -142,6 +142,28 @@ def test_large_region_matcher_equals_general_kernel(size, speckle, vmax):
             assert np.array_equal(ballots[fld], outs[0][1][fld]), fld
 
 
+def test_large_region_matcher_epoch_wrap(monkeypatch):
+    """The bucket heads of rb_kpm_big_kernel carry a 16-bit epoch instead of being cleared; started just below the
+    wrap, every CTA crosses it within a few work items and must zero its tables exactly once."""
+    n = 120
+    seq = synth.scrolling_tilemap(n, 640, 480, seed=405, speckle=0.08, vmax=(30, 30))
+    with remap_b200.Registrar(640, 480, max_frames=n, run_pairs=4) as reg:
+        reg.upload(seq.frames)
+        off_a, _ = reg.register(n)
+        ballots_a = reg.fetch_ballots(n - 1)
+    monkeypatch.setenv("RB_BIG_EPOCH0", "65530")  # first work item fits below the wrap, the second crosses it
+    with remap_b200.Registrar(640, 480, max_frames=n, run_pairs=4) as reg:
+        assert reg.matcher_kernel == "rb_kpm_big_kernel"
+        reg.upload(seq.frames)
+        off_b, _ = reg.register(n)
+        ballots_b = reg.fetch_ballots(n - 1)
+        assert reg.deferred_count == 0
+    assert np.array_equal(off_a, off_b)
+    for fld in ballots_a.dtype.names:
+        assert np.array_equal(ballots_a[fld], ballots_b[fld]), fld
+    assert np.array_equal(np.stack([off_a["dx"], off_a["dy"]], 1), seq.true_offsets)
+
+
 def test_pipelined_matcher_defers_nothing_on_config2_frames():
     n = 500
     seq = synth.scrolling_tilemap(n, 320, 224, seed=1)
