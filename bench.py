@@ -446,13 +446,13 @@ def main():
             if world > 1:
                 gathered["off"] = shard.gather_offsets(host_off, total_frames, device=dev)
 
-        for _ in range(min(args.warmup, 2)):
-            e2e_step()
+        for _ in range(args.warmup):  # the same W warm-up steps as the device-timed region (first steps also pay the
+            e2e_step()                # host's page pinning / IOMMU mappings and the rate estimates settling)
         sync_all()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        esteps = max(2, min(args.steps, 5))
+        esteps = max(2, min(args.steps, 10))
         step_s = []
         for _ in range(esteps):
             ts = time.perf_counter()

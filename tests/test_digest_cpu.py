@@ -49,3 +49,22 @@ def test_sharded_digest_and_stitched_collector_positions(threads):
     dump = refdump.ref_dump(seq.frames)
     assert np.array_equal(ref["positions"], dump["positions"])
     assert len(np.unique(ref["positions"][:, 0])) >= 2
+
+
+def test_pairs_mode_equals_digest_declarations(tmp_path):
+    """ref_harness pairs (what tools/resolve_flagged.py replays flagged pairs with) declares what the digest's kpm::match
+    declared for the same pairs."""
+    import os
+    import subprocess
+    n, W, H = 12, 320, 224
+    seq = synth.scrolling_tilemap(n, W, H, seed=63, cut_every=4)
+    ref = digest_check.ref_digest(seq.frames, threads=2, collector=False)
+    fin, pin, pout = (os.path.join(tmp_path, x) for x in ("f.bin", "p.bin", "o.bin"))
+    seq.frames.tofile(fin)
+    pairs = np.array([0, 3, 4, 7, 10], np.uint32)
+    pairs.tofile(pin)
+    subprocess.check_call([digest_check.REF_BIN, "pairs", fin, str(W), str(H), str(n), pin, pout])
+    res = np.fromfile(pout, "<i4").reshape(-1, 3)
+    rp = ref["pairs"][pairs]
+    assert np.array_equal(res[:, 0] != 0, rp["valid"] != 0)
+    assert np.array_equal(res[:, 1], rp["dx"]) and np.array_equal(res[:, 2], rp["dy"])
