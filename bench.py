@@ -485,6 +485,7 @@ def main():
                "h2d_bytes_per_step": int(lanes["h2d_bytes"]),
                "host_input_bytes_per_step": int(n * args.width * args.height),
                "d2h_bytes_per_step": int((n - 1) * 12),
+               "bytes_scope": "rank 0's share (every rank moves the same amount)",
                "steps": esteps, "warmup_steps": e2e_warmup_steps, "step_seconds": step_s, "lanes": lanes,
                "note": "rb_register_host_async from pinned host frames (per chunk: raw copy + device pack, or host pack + half the "
                        "bytes; copies on a second stream under the kernels of earlier chunks) + rb_fetch_offsets per step; wall "
