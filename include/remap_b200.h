@@ -54,10 +54,12 @@ typedef struct rb_config {
   uint32_t offset_slots;    /* 0 = auto; shared-memory offset table slots (power of two)   */
   uint32_t profile;         /* 1: record CUDA events around every kernel (rb_kernel_times) */
   void* stream;             /* cudaStream_t to use, or NULL to create one                  */
-  uint32_t kpm_mode;        /* 0 = pipelined matcher, general kernel for what it defers;
-                               1 = general kernel only (one CTA per pair and region)         */
-  uint32_t list_cap;        /* 0 = auto; per-region keypoint list capacity of the pipelined
-                               matcher (<= 2047); longer lists are deferred                   */
+  uint32_t kpm_mode;        /* 0 = pipelined matchers (which of the two takes the regions first follows the
+                               region size), general kernel for what they defer; 1 = general kernel only (one
+                               CTA per pair and region); 2 / 3 = large-region / fast pipelined matcher first */
+  uint32_t list_cap;        /* 0 = auto; per-region keypoint list capacity of the first-pass pipelined
+                               matcher (<= 2047); longer lists go to the large-region matcher (second pass,
+                               up to 2 x list_cap), then to the general kernel                              */
   uint32_t run_pairs;       /* 0 = auto; consecutive pairs per work item of the matcher      */
   uint32_t upload_chunk;    /* 0 = auto; frames per host->device chunk of rb_register_host_async */
   uint32_t overlap_batches; /* 0 = auto (1 = K1 then matcher, one after the other); > 1: batches per call, K1 of
