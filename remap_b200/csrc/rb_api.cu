@@ -443,7 +443,7 @@ struct rb_ctx {
   cudaEvent_t ev_kpe[RB_MAX_BATCHES];
   cudaStream_t copy_stream;  // host -> device copies of rb_register_host_async
   cudaEvent_t ev_copy[2], ev_entry;
-  uint8_t* h_stage[2];     // pinned staging: two chunks of packed 4 bit/pixel frames
+  uint8_t* h_stage[3];     // pinned staging: chunks of packed 4 bit/pixel frames (RB_STAGE_BUFS of them in use, default 3)
   uint32_t* h_flags;       // pinned: copy of d_work[0..3] fetched with the offsets ([2] = matcher error word)
   // rb_register_host_async: one "landed" event per chunk (timing enabled: the link rate is estimated from them)
   std::vector<cudaEvent_t> ev_chunk, ev_chunk_start;
@@ -783,7 +783,7 @@ void rb_destroy(rb_ctx* c) {
   for (int i = 0; i < 2; ++i)
     if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
   if (c->ev_entry) cudaEventDestroy(c->ev_entry);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
   if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1186,9 +1186,9 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
   RB_CUDA(c, cudaSetDevice(c->device));
   const RbGeom& g = c->g;
-  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 1024;
+  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 512;
   // Chunk sizes: `chunk` frames each, but a long call ramps up (128, 256, ... frames) and down again, so that the
-  // link starts after packing 128 frames, not 1,024, and the last copy + kernels that nothing overlaps are short.
+  // link starts after packing 128 frames, not 512, and the last copy + kernels that nothing overlaps are short.
   std::vector<size_t> sizes;
   {
     std::vector<size_t> ramp;
@@ -1214,8 +1214,12 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   // (2.59 M frames/s on 8 GPUs against 1.22 M all packed and 2.13 M mixed).
   if (pinned && host_share() >= 4) lane_force = 1;
   if (const char* e = getenv("RB_HOST_LANE")) lane_force = !strcmp(e, "raw") ? 1 : !strcmp(e, "packed") ? 2 : !strcmp(e, "auto") ? 0 : lane_force;
+  // Two staging buffers of 512 frames (2 x 18 MB at 320x224) stay in a 60 MB last-level cache, from where the DMA engine
+  // reads them; measured: a third buffer (RB_STAGE_BUFS=3) or 1,024-frame chunks cost 10 % (1.13 -> 1.01 / 0.98 M frames/s).
+  int nstage = 2;
+  if (const char* e = getenv("RB_STAGE_BUFS")) { const int v = atoi(e); if (v == 2 || v == 3) nstage = v; }
   if (have4 && c->stage_frames < chunk) {  // (no chunk is larger than `chunk`)
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
       RB_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&c->h_stage[i]), c->frame_stride4 * chunk, cudaHostAllocDefault));
     }
@@ -1234,7 +1238,7 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   size_t oldest = 0;          // first chunk whose copy may still be in flight
   double inflight_bytes = 0;  // bytes queued on the link and not yet known to have landed
   std::vector<double> chunk_bytes(nchunks, 0.0);
-  int stage_owner[2] = {-1, -1};  // chunk whose packed copy last read staging buffer i
+  int stage_owner[3] = {-1, -1, -1};  // chunk whose packed copy last read staging buffer i
   int stage_next = 0;
   size_t at = 0;
   for (size_t k = 0; k < nchunks; at += sizes[k], ++k) {
@@ -1271,7 +1275,7 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
       ++c->lane_raw;
     } else {
       const int sb = stage_next;
-      stage_next ^= 1;
+      stage_next = (stage_next + 1) % nstage;
       if (stage_owner[sb] >= 0) RB_CUDA(c, cudaEventSynchronize(c->ev_chunk[stage_owner[sb]]));  // staging buffer free again
       timespec t0, t1;
       clock_gettime(CLOCK_MONOTONIC, &t0);
