@@ -1186,7 +1186,12 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
   RB_CUDA(c, cudaSetDevice(c->device));
   const RbGeom& g = c->g;
-  const size_t chunk = c->cfg.upload_chunk ? c->cfg.upload_chunk : 512;
+  // frames per chunk: what keeps a staging buffer at ~18 MB (see the staging buffers below), 128 ... 512
+  size_t chunk = c->cfg.upload_chunk;
+  if (!chunk) {
+    chunk = (size_t)(18.4e6 / (double)(c->frame_stride4 ? c->frame_stride4 : g.frame_stride / 2 + 1)) / 64 * 64;
+    chunk = chunk < 128 ? 128 : chunk > 512 ? 512 : chunk;
+  }
   // Chunk sizes: `chunk` frames each, but a long call ramps up (128, 256, ... frames) and down again, so that the
   // link starts after packing 128 frames, not 512, and the last copy + kernels that nothing overlaps are short.
   std::vector<size_t> sizes;
