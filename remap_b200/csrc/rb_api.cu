@@ -1181,6 +1181,21 @@ static int chunk_landed(rb_ctx* c, size_t first, size_t at, size_t m, bool arriv
 // (bytes still queued on the link / measured link rate < chunk frames / measured packer rate).  With many host threads per GPU nearly
 // everything goes packed (the link is the limit and packed halves its load); with few threads per GPU (one rank of
 // eight on a node) nearly everything goes raw.  Copies of later chunks run under the kernels of earlier ones.
+struct RbPendingChunk {  // a landed chunk whose kernels have not been launched yet
+  rb_ctx* c;
+  size_t first, at, m;
+  bool packed, live;
+  cudaEvent_t landed;
+  int rc;
+};
+static void flush_pending(void* arg) {
+  RbPendingChunk* p = static_cast<RbPendingChunk*>(arg);
+  if (!p->live) return;
+  p->live = false;
+  const int rc = chunk_landed(p->c, p->first, p->at, p->m, p->packed, p->landed);
+  if (rc != RB_OK) p->rc = rc;
+}
+
 int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_t n) {
   if (!c || !frames) return RB_ERR_INVALID;
   if (n < 1 || first + n > c->cfg.max_frames) { c->err = "rb_register_host: frame range"; return RB_ERR_CAPACITY; }
@@ -1243,6 +1258,9 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   size_t oldest = 0;          // first chunk whose copy may still be in flight
   double inflight_bytes = 0;  // bytes queued on the link and not yet known to have landed
   std::vector<double> chunk_bytes(nchunks, 0.0);
+  RbPendingChunk pending;
+  pending.c = c; pending.first = first; pending.at = pending.m = 0; pending.packed = pending.live = false; pending.landed = nullptr;
+  pending.rc = RB_OK;
   int stage_owner[3] = {-1, -1, -1};  // chunk whose packed copy last read staging buffer i
   int stage_next = 0;
   size_t at = 0;
@@ -1284,8 +1302,11 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
       if (stage_owner[sb] >= 0) RB_CUDA(c, cudaEventSynchronize(c->ev_chunk[stage_owner[sb]]));  // staging buffer free again
       timespec t0, t1;
       clock_gettime(CLOCK_MONOTONIC, &t0);
-      rb_hostpack_frames(frames + (size_t)g.W * g.H * at, g.W, g.H, m, c->h_stage[sb], c->pitch4, pack_threads);
+      // the previous chunk's kernel launches ride along: issued by this thread while the other packer threads already work
+      rb_hostpack_frames_cb(frames + (size_t)g.W * g.H * at, g.W, g.H, m, c->h_stage[sb], c->pitch4, pack_threads,
+                            pending.live ? flush_pending : nullptr, &pending);
       clock_gettime(CLOCK_MONOTONIC, &t1);
+      if (pending.rc != RB_OK) return pending.rc;
       const double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
       if (dt > 0) { const double fps = m / dt; c->pack_fps = c->pack_fps > 0 ? 0.7 * c->pack_fps + 0.3 * fps : fps; }
       RB_CUDA(c, cudaEventRecord(c->ev_chunk_start[k], c->copy_stream));
@@ -1298,8 +1319,15 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
     RB_CUDA(c, cudaEventRecord(landed, c->copy_stream));
     inflight_bytes += chunk_bytes[k];
     c->lane_bytes += (uint64_t)chunk_bytes[k];
-    rc = chunk_landed(c, first, at, m, !raw, landed);
-    if (rc != RB_OK) return rc;
+    // the device side of this chunk (stream-ordered behind its copy) is launched with the NEXT chunk's packing, or at once
+    // when nothing will be packed next (raw chunks, the last chunk)
+    flush_pending(&pending);
+    if (pending.rc != RB_OK) return pending.rc;
+    pending.live = true; pending.at = at; pending.m = m; pending.packed = !raw; pending.landed = landed;
+    if (raw || k + 1 == nchunks) {
+      flush_pending(&pending);
+      if (pending.rc != RB_OK) return pending.rc;
+    }
   }
   note_registered(c, first, n);
   return RB_OK;

@@ -44,7 +44,8 @@ static inline void pack_row(const uint8_t* src, uint32_t W, uint8_t* dst, uint32
   if (x / 2 < pitch4) memset(dst + x / 2, 0, pitch4 - x / 2);
 }
 
-void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4, int threads) {
+void rb_hostpack_frames_cb(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4, int threads,
+                           void (*pre)(void*), void* arg) {
   const long long rows = (long long)n * H;
   // an explicit count: launchers such as torchrun export OMP_NUM_THREADS=1, which would serialise the packer
   int nt = threads > 0 ? threads : omp_get_num_procs();
@@ -54,14 +55,35 @@ void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n,
   // every packed byte to DRAM and back -- the host's DRAM bandwidth is what bounds the packer).  RB_PACK_STREAM=1
   // selects the non-temporal variant (hosts with a small cache).
   static const bool stream = getenv("RB_PACK_STREAM") && atoi(getenv("RB_PACK_STREAM")) != 0;
-  if (stream) {
+  // `pre` runs on the CALLING thread (the team's thread 0) while the others already pack: the caller's kernel
+  // launches for the previous chunk cost it tens of microseconds per chunk that would otherwise idle the whole team.
+  // Rows are handed out dynamically, so thread 0 simply joins late.
+  static const bool sched_static = getenv("RB_PACK_STATIC") && atoi(getenv("RB_PACK_STATIC")) != 0;  // experiments
+  if (sched_static) {
+    if (pre) pre(arg);
 #pragma omp parallel for schedule(static) num_threads(nt)
-    for (long long r = 0; r < rows; ++r) pack_row<true>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+    for (long long r = 0; r < rows; ++r) {
+      if (stream) pack_row<true>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+      else pack_row<false>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+    }
   } else {
-#pragma omp parallel for schedule(static) num_threads(nt)
-    for (long long r = 0; r < rows; ++r) pack_row<false>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+#pragma omp parallel num_threads(nt)
+    {
+      if (pre && omp_get_thread_num() == 0) pre(arg);
+      if (stream) {
+#pragma omp for schedule(dynamic, 64)
+        for (long long r = 0; r < rows; ++r) pack_row<true>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+      } else {
+#pragma omp for schedule(dynamic, 64)
+        for (long long r = 0; r < rows; ++r) pack_row<false>(frames + (size_t)r * W, W, dst + (size_t)r * pitch4, pitch4);
+      }
+    }
   }
 #if defined(__AVX2__)
-  _mm_sfence();  // the streaming stores must be visible before the copy is queued
+  _mm_sfence();  // streaming stores must be visible before the copy is queued
 #endif
+}
+
+void rb_hostpack_frames(const uint8_t* frames, uint32_t W, uint32_t H, size_t n, uint8_t* dst, uint32_t pitch4, int threads) {
+  rb_hostpack_frames_cb(frames, W, H, n, dst, pitch4, threads, nullptr, nullptr);
 }
