@@ -640,7 +640,7 @@ int rb_create(const rb_config* cfg, rb_ctx** out) {
     f.lcap = 2 * cap;  // list rows hold all keypoints of a region even when only the weight-2 ones take part
     f.tslots = next_pow2(cap < 2048 ? (cap < 64 ? 64 : (cap > 1024 ? 2048 : 2 * cap)) : cap);  // chained buckets: load <= 1 is fine
     f.oslots = 1024;
-    f.run = cfg->run_pairs ? cfg->run_pairs : 32;
+    f.run = cfg->run_pairs ? cfg->run_pairs : 40;  // auto: 8 ... 40 pairs per work item, chosen per launch (pick_run); shared memory sized for 40
     int smem_max = 0;
     RB_CUDA(c, cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->fast_smem = rbf::smem_bytes(f);
@@ -946,6 +946,24 @@ static int launch_kpe(rb_ctx* c, size_t f0, size_t kn, cudaStream_t st) {
 // The matcher + K3 for the n - 1 pairs of frames [first, first + n), on the main stream.  Frames
 // [list_first, first + n) still need their region lists (K1c).  Ballots, results and offsets are stored at
 // the pair's absolute index (= index of its first frame).
+// Pairs per work item of a pipelined matcher launch.  The CTAs take (region, run) items off one queue; the launch ends
+// when the last item does, so what counts is whole WAVES of items: ceil(items / CTAs) waves of run + 1 steps each (a run
+// of r pairs walks r + 1 frames).  Among 8 ... 40 pairs per run (longer runs would leave too few items to even out the
+// regions' different sizes), the cheapest in those terms: 4,999 pairs of 8 regions on 148 CTAs: 34 pairs -> 148 runs ->
+// exactly 8 waves of 35 steps, against 9 waves of 33 with 32; a 512-frame chunk of the host path: 10 pairs -> 416 items
+// on 296 CTAs instead of 128.
+static uint32_t pick_run(const rb_ctx* c, uint32_t npairs, uint32_t nreg, uint32_t ctas) {
+  if (c->cfg.run_pairs) return c->cfg.run_pairs;
+  uint32_t best = 32;
+  double best_cost = 1e300;
+  for (uint32_t r = 8; r <= 40; ++r) {
+    const uint32_t runs = (npairs + r - 1) / r, items = runs * nreg, waves = (items + ctas - 1) / ctas;
+    const double cost = (double)waves * (r + 1);
+    if (cost < best_cost * 0.999) { best_cost = cost; best = r; }
+  }
+  return best;
+}
+
 static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cudaEvent_t* ev) {
   const RbGeom& g = c->g;
   if (ev) RB_CUDA(c, cudaEventRecord(ev[2], c->stream));
@@ -988,6 +1006,7 @@ static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cu
         f.deferred_count = c->d_work + 4;  // per-launch list position; d_work[1] keeps the running total
         f.deferred = c->d_deferred;
         f.items = nullptr; f.nitems = nullptr;
+        f.run = pick_run(c, f.npairs, g.nreg, (uint32_t)c->sm_count);
         const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
         uint32_t grid = (uint32_t)c->sm_count;
         if (grid > witems) grid = witems;
@@ -1000,6 +1019,7 @@ static int launch_match(rb_ctx* c, size_t first, size_t n, size_t list_first, cu
         f.deferred_count = c->d_work + 4;
         f.deferred = c->d_deferred;
         f.items = nullptr; f.nitems = nullptr;
+        f.run = pick_run(c, f.npairs, g.nreg, (uint32_t)(c->sm_count * c->fast_ctas_per_sm));
         const uint32_t witems = ((f.npairs + f.run - 1) / f.run) * g.nreg;
         uint32_t grid = (uint32_t)(c->sm_count * c->fast_ctas_per_sm);
         if (grid > witems) grid = witems;
