@@ -1267,6 +1267,8 @@ int rb_register_host_async(rb_ctx* c, const uint8_t* frames, size_t first, size_
   }
   int rc = ensure_chunk_events(c, nchunks);
   if (rc != RB_OK) return rc;
+  // a previous call's packed copies may still be reading the staging buffers (callers need not synchronise in between)
+  RB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   const int pack_threads = packer_threads(c);
   // the copies must not overtake earlier work on the main stream that still reads these slots
   RB_CUDA(c, cudaEventRecord(c->ev_entry, c->stream));

@@ -496,3 +496,25 @@ def test_aws_compare_single_frame_and_identical_frames():
         assert heat.min() == 1 and (fc == 0xFFFFFFFF).all()
         heat, fc = reg.aws_compare(5)               # five identical frames: nothing ever changes
         assert heat.min() == 1 and (fc == 0xFFFFFFFF).all()
+
+
+def test_back_to_back_host_registrations_without_a_fetch_in_between():
+    """Two rb_register_host_async calls in a row (no synchronising call between them): the second must not pack into
+    staging memory the first call's copies are still reading."""
+    import torch
+    n, W, H = 1200, 320, 224
+    seq = synth.scrolling_tilemap(2 * n, W, H, seed=94)
+    a = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    b = torch.empty((n, H, W), dtype=torch.uint8, pin_memory=True)
+    a.numpy()[...] = seq.frames[:n]
+    b.numpy()[...] = seq.frames[n:]
+    with remap_b200.Registrar(W, H, max_frames=2 * n, upload_chunk=64) as reg:
+        reg.upload(seq.frames)
+        want, _ = reg.register(2 * n)
+    with remap_b200.Registrar(W, H, max_frames=2 * n, upload_chunk=64) as reg:
+        reg.register_host_async(a.numpy(), first=0)
+        reg.register_host_async(b.numpy(), first=n)
+        got_b = reg.fetch_offsets(n - 1)
+        reg.register_async(2 * n)  # the frames of both calls are resident and intact
+        got = reg.fetch_offsets(2 * n - 1)
+    assert np.array_equal(got_b, want[n:]) and np.array_equal(got, want)
