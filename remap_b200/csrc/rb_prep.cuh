@@ -158,11 +158,12 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
     uint32_t* out = lists + ((uint64_t)frame * g.nreg + region) * cap;
     uint32_t b2 = 0, b1 = 0;
     if (L.rows_per_chunk != 0) {
-      uint32_t kw, ww;
+      uint32_t kw, ww, nkw, nww;  // this chunk's words and the next one's; the one after that is requested below
       rbl::lane_words(g, L, kpf, w2f, 0, kw, ww);
+      rbl::lane_words(g, L, kpf, w2f, L.rows_per_chunk, nkw, nww);
       for (uint32_t ra = 0; ra < L.nrows; ra += L.rows_per_chunk) {
-        uint32_t nkw, nww;  // next chunk's words, requested before this chunk is worked on
-        rbl::lane_words(g, L, kpf, w2f, ra + L.rows_per_chunk, nkw, nww);
+        uint32_t nnkw, nnww;  // two chunks ahead: the emit loops below are short, one chunk of lead did not cover the loads
+        rbl::lane_words(g, L, kpf, w2f, ra + 2 * L.rows_per_chunk, nnkw, nnww);
         const uint32_t c = __popc(ww) | (__popc(kw & ~ww) << 16);  // weight-2 / weight-1 counts in one word
         uint32_t incl = c;
 #pragma unroll
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256) rb_list_kernel(const RbGeom g, const uint
         b2 += tot & 0xFFFFu;
         b1 += tot >> 16;
         kw = nkw; ww = nww;
+        nkw = nnkw; nww = nnww;
       }
     } else {
       b2 = b1 = cap + 1;  // not listed: forces the matcher to defer this region
