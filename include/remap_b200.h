@@ -60,7 +60,7 @@ typedef struct rb_config {
   uint32_t list_cap;        /* 0 = auto; per-region keypoint list capacity of the first-pass pipelined
                                matcher (<= 2047); longer lists go to the large-region matcher (second pass,
                                up to 2 x list_cap), then to the general kernel                              */
-  uint32_t run_pairs;       /* 0 = auto; consecutive pairs per work item of the matcher      */
+  uint32_t run_pairs;       /* 0 = auto (8..40, per launch); consecutive pairs per work item of the matcher */
   uint32_t upload_chunk;    /* 0 = auto; frames per host->device chunk of rb_register_host_async */
   uint32_t overlap_batches; /* 0 = auto (1 = K1 then matcher, one after the other); > 1: batches per call, K1 of
                                batch b + 1 on a second stream concurrently with the matcher of batch b (slower
